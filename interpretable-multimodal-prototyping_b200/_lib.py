@@ -1,0 +1,71 @@
+"""ctypes binding of libimp_sm100.so (include/imp_hotpath.h).  There is no CPU or eager
+fallback: if the library is missing it is built with nvcc, and if that fails import fails."""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(HERE), "include", "imp_hotpath.h")
+LIB_PATH = os.path.join(HERE, "libimp_sm100.so")
+
+_lib = None
+
+
+class ImpError(RuntimeError):
+    pass
+
+
+def header_symbols(header: str = HEADER):
+    """Names of every function include/imp_hotpath.h declares."""
+    text = open(header).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(imp_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            from . import build as _build
+            _build.build()
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.imp_last_error.restype = ctypes.c_char_p
+        _lib.imp_abi_version.restype = ctypes.c_int
+        for name in header_symbols():
+            fn = getattr(_lib, name)          # AttributeError if the .so lacks a declared symbol
+            if name.endswith("_bytes"):
+                fn.restype = ctypes.c_size_t
+    return _lib
+
+
+def _conv(a):
+    import torch
+    if a is None:
+        return ctypes.c_void_p(0)
+    if isinstance(a, torch.Tensor):
+        return ctypes.c_void_p(a.data_ptr())
+    if isinstance(a, bool):
+        return ctypes.c_int(int(a))
+    if isinstance(a, int):
+        return ctypes.c_int(a)
+    if isinstance(a, float):
+        return ctypes.c_float(a)
+    return a
+
+
+def call(name: str, *args) -> None:
+    """Call an int-returning entry point; raise ImpError with the library's message on failure."""
+    rc = getattr(lib(), name)(*[_conv(a) for a in args])
+    if rc != 0:
+        raise ImpError("%s failed (%d): %s" % (name, rc, lib().imp_last_error().decode()))
+
+
+def query(name: str, *args) -> int:
+    return int(getattr(lib(), name)(*[_conv(a) for a in args]))
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

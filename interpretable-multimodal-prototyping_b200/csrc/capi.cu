@@ -1,0 +1,77 @@
+// C-ABI of libimp_sm100.so (declared in include/imp_hotpath.h).
+// Plain pointers + sizes + a cudaStream_t passed as void*; int status (0 = ok), message via
+// imp_last_error().  No allocation, no ownership transfer, no torch types.
+#include "common.cuh"
+#include "launchers.h"
+#include "../../include/imp_hotpath.h"
+
+thread_local char g_imp_err[512] = {0};
+
+extern "C" const char* imp_last_error(void) { return g_imp_err; }
+extern "C" int imp_abi_version(void) { return IMP_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------
+// driver entry point for cuTensorMapEncodeTiled, resolved lazily so the library has no link-time
+// dependency on libcuda (it must load on a GPU-less build box for the symbol check)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode_fn() {
+  static encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_tiled_fn>(p);
+  }
+  return fn;
+}
+
+int imp_make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elt_bytes, uint64_t inner,
+                     uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer,
+                     CUtensorMapSwizzle swz) {
+  encode_tiled_fn fn = get_encode_fn();
+  if (!fn) IMP_FAIL(IMP_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) IMP_FAIL(IMP_ERR_ARG, "tensor base %p not 16-byte aligned", base);
+  if (row_stride_bytes % 16 != 0) IMP_FAIL(IMP_ERR_ARG, "row stride %llu not a multiple of 16 B", (unsigned long long)row_stride_bytes);
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  (void)elt_bytes;
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) IMP_FAIL(IMP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return IMP_OK;
+}
+
+int imp_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+// ------------------------------------------------------------------------------------------
+// A1 path_net
+// ------------------------------------------------------------------------------------------
+extern "C" int imp_pathnet_fwd(const void* x, const void* w1, const float* b1, void* h, int rows, int in_features,
+                               float p_drop, unsigned seed, void* stream) {
+  if (!x || !w1 || !b1 || !h) IMP_FAIL(IMP_ERR_ARG, "imp_pathnet_fwd: null pointer");
+  return launch_pathnet_fwd((const bf16*)x, (const bf16*)w1, b1, (bf16*)h, rows, in_features, p_drop, seed, ST(stream));
+}
+
+extern "C" size_t imp_pathnet_dw_workspace_bytes(int in_features) { return pathnet_dw_workspace_bytes(in_features); }
+
+extern "C" int imp_pathnet_dw(const void* dz, const void* x, float* dw1, void* workspace, int rows, int in_features,
+                              int accumulate, void* stream) {
+  if (!dz || !x || !dw1 || !workspace) IMP_FAIL(IMP_ERR_ARG, "imp_pathnet_dw: null pointer");
+  return launch_pathnet_dw((const bf16*)dz, (const bf16*)x, dw1, (float*)workspace, rows, in_features, accumulate, ST(stream));
+}

@@ -177,6 +177,7 @@ struct DwParams {
   int kin;            // 512
   int ksplit;
   int kblocks_total;  // ceil(rows/64)
+  uint32_t lbo, sbo;  // MN-major descriptor strides
 };
 
 __global__ void __launch_bounds__(kDwThreads, 1)
@@ -241,8 +242,8 @@ pathnet_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
 #pragma unroll
         for (int k = 0; k < kDwBK / 16; ++k) {
           // MN-major: LBO = stride between 64-wide MN boxes (8 KB), SBO = 8 k-rows (1 KB)
-          uint64_t ad = umma_desc_sw128(sa + k * 2048, kDwBK * 128, 1024);
-          uint64_t bd = umma_desc_sw128(sb + k * 2048, kDwBK * 128, 1024);
+          uint64_t ad = umma_desc_sw128(sa + k * 2048, p.lbo, p.sbo);
+          uint64_t bd = umma_desc_sw128(sb + k * 2048, p.lbo, p.sbo);
           umma_f16(tmem_base, ad, bd, idesc, (i | k) != 0);
         }
         umma_commit(&empty[stage]);
@@ -361,6 +362,7 @@ int launch_pathnet_dw(const bf16* dz, const bf16* x, float* dw, float* workspace
   p.partial = workspace; p.rows = rows; p.kin = kin;
   p.kblocks_total = (rows + kDwBK - 1) / kDwBK;
   p.ksplit = max(1, min(imp_num_sms() / ntile, p.kblocks_total));
+  p.lbo = kDwBK * 128; p.sbo = 1024;
   static bool attr_done = false;
   if (!attr_done) {
     IMP_CUDA(cudaFuncSetAttribute(pathnet_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem));
