@@ -36,6 +36,34 @@ size_t imp_pathnet_dw_workspace_bytes(int in_features);
 int imp_pathnet_dw(const void* dz, const void* x, float* dw1, void* workspace, int rows, int in_features,
                    int accumulate, void* stream);
 
+/* A2/A3  softmax pooling of the patches of each bag into P prototype tokens (keys = values = h):
+ *   medmm/modeling/models/umeml_gan.py:65-80,425-434 ; medmm/modeling/ops/attention.py:345-533
+ * With the folded query qt = ((c Wq^T + bq)/16) Wk (P,256) [attention.py:368,382,432,509]:
+ *   S = qt h^T ; a = softmax over patches [attention.py:527] ; pooled = a h [attention.py:530]
+ * h (total_rows,256) bf16, bags packed back to back; cu_seqlens (n_bags+1) int32 row offsets;
+ * max_len >= the longest bag (host-side bound used for the launch grid; no device sync);
+ * qt (n_bags or 1, P, 256) fp32 with qt_bag_stride elements between bags (0 = shared queries);
+ * pooled (n_bags,P,256) fp32, lse (n_bags,P) fp32 = log sum_n exp(S).  1 <= P <= 64. */
+size_t imp_pool_fwd_workspace_bytes(int n_bags, int max_len, int n_proto);
+int imp_pool_fwd(const void* h, int total_rows, const int* cu_seqlens, int n_bags, int max_len,
+                 const float* qt, long long qt_bag_stride, int n_proto, void* workspace, float* pooled,
+                 float* lse, void* stream);
+
+/* backward of n_blocks (1 or 2) stacked pooling blocks that share h (autograd of the lines above).
+ * Per block k (HOST arrays of n_blocks device pointers): qt[k], dpooled[k] (n_bags,P,256), lse[k],
+ * delta[k] (n_bags,P) with delta = rowsum(dpooled * pooled).
+ * dq (n_bags,P,256) fp32 <- gradient wrt qt[dq_block].
+ * If dz != NULL also: dz (total_rows,256) bf16 <- dL/dh summed over the blocks when relu_mask = 0,
+ * or keep_scale * [h>0] * dL/dh (the gradient at the pre-activation of path_net, umeml_gan.py:266-268)
+ * when relu_mask = 1; and db1 (256) (+)= column sums of dz. */
+size_t imp_pool_bwd_workspace_bytes(int n_bags, int max_len, int n_proto);
+int imp_pool_bwd(const void* h, int total_rows, const int* cu_seqlens, int n_bags, int max_len,
+                 int n_blocks, const float* const* qt, const long long* qt_bag_stride,
+                 const float* const* dpooled, const float* const* lse, const float* const* delta,
+                 int n_proto, int dq_block, int relu_mask, float keep_scale, void* workspace, float* dq,
+                 void* dz,
+                 float* db1, int db_accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

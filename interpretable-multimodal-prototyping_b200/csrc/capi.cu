@@ -75,3 +75,31 @@ extern "C" int imp_pathnet_dw(const void* dz, const void* x, float* dw1, void* w
   if (!dz || !x || !dw1 || !workspace) IMP_FAIL(IMP_ERR_ARG, "imp_pathnet_dw: null pointer");
   return launch_pathnet_dw((const bf16*)dz, (const bf16*)x, dw1, (float*)workspace, rows, in_features, accumulate, ST(stream));
 }
+
+// ------------------------------------------------------------------------------------------
+// A2/A3 softmax pooling into prototype tokens
+// ------------------------------------------------------------------------------------------
+extern "C" size_t imp_pool_fwd_workspace_bytes(int n_bags, int max_len, int n_proto) {
+  return pool_fwd_workspace_bytes(n_bags, max_len, n_proto);
+}
+extern "C" int imp_pool_fwd(const void* h, int total_rows, const int* cu_seqlens, int n_bags, int max_len,
+                            const float* qt, long long qt_bag_stride, int n_proto, void* workspace, float* pooled,
+                            float* lse, void* stream) {
+  if (!h || !cu_seqlens || !qt || !workspace || !pooled || !lse) IMP_FAIL(IMP_ERR_ARG, "imp_pool_fwd: null pointer");
+  return launch_pool_fwd((const bf16*)h, total_rows, cu_seqlens, n_bags, max_len, qt, qt_bag_stride, n_proto,
+                         (float*)workspace, pooled, lse, ST(stream));
+}
+extern "C" size_t imp_pool_bwd_workspace_bytes(int n_bags, int max_len, int n_proto) {
+  return pool_bwd_workspace_bytes(n_bags, max_len, n_proto);
+}
+extern "C" int imp_pool_bwd(const void* h, int total_rows, const int* cu_seqlens, int n_bags, int max_len,
+                            int n_blocks, const float* const* qt, const long long* qt_bag_stride,
+                            const float* const* dpooled, const float* const* lse, const float* const* delta,
+                            int n_proto, int dq_block, int relu_mask, float keep_scale, void* workspace, float* dq, void* dz,
+                            float* db1, int db_accumulate, void* stream) {
+  if (!h || !cu_seqlens || !qt || !qt_bag_stride || !dpooled || !lse || !delta || !workspace || !dq)
+    IMP_FAIL(IMP_ERR_ARG, "imp_pool_bwd: null pointer");
+  return launch_pool_bwd((const bf16*)h, total_rows, cu_seqlens, n_bags, max_len, n_blocks, qt, qt_bag_stride, dpooled,
+                         lse, delta, n_proto, dq_block, relu_mask, keep_scale, (float*)workspace, dq, (bf16*)dz, db1,
+                         db_accumulate, ST(stream));
+}

@@ -10,3 +10,13 @@ int launch_pathnet_dw(const bf16* dz, const bf16* x, float* dw, float* workspace
                       cudaStream_t st);
 int launch_sum_partials(const float* partial, float* out, int nsplit, size_t n, float scale, int accumulate,
                         cudaStream_t st);
+
+// pool.cu
+size_t pool_fwd_workspace_bytes(int B, int max_len, int P);
+int launch_pool_fwd(const bf16* h, int total_rows, const int* cu, int B, int max_len, const float* qt,
+                    long long qt_stride, int P, float* workspace, float* pooled, float* lse, cudaStream_t st);
+size_t pool_bwd_workspace_bytes(int B, int max_len, int P);
+int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max_len, int nblocks,
+                    const float* const* qt, const long long* qt_stride, const float* const* dpool,
+                    const float* const* lse, const float* const* delta, int P, int dq_block, int relu_mask,
+                    float keep_scale, float* workspace, float* dq, bf16* dz, float* db1, int db_accumulate, cudaStream_t st);

@@ -1,0 +1,111 @@
+"""Thin tensor-level wrappers over the C-ABI (one function per ``imp_*`` entry point).
+
+These only validate shapes/dtypes, allocate outputs and workspaces through torch's caching
+allocator and pass raw device pointers plus the current CUDA stream.  No arithmetic happens
+in Python and there is no fallback path: every function requires CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+D = 256           # MODEL.HIDDEN_DIM (umeml_gan.py:247)
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.ImpError("%s must be a CUDA tensor: the IMP hot path has no CPU implementation" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s: expected %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def _ptr_array(tensors: Sequence[torch.Tensor]):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def pathnet_fwd(x: torch.Tensor, w1_bf16: torch.Tensor, b1: torch.Tensor, p_drop: float = 0.0,
+                seed: int = 0) -> torch.Tensor:
+    """h = Dropout(ReLU(x W1^T + b1)) -> (rows,256) bf16   [umeml_gan.py:266-268,410]."""
+    _chk(x, torch.bfloat16, "x"); _chk(w1_bf16, torch.bfloat16, "w1"); _chk(b1, torch.float32, "b1")
+    rows, kin = x.shape
+    h = torch.empty(rows, D, device=x.device, dtype=torch.bfloat16)
+    if rows:
+        _lib.call("imp_pathnet_fwd", x, w1_bf16, b1, h, rows, kin, float(p_drop), int(seed) & 0x7FFFFFFF,
+                  _lib.stream_ptr())
+    return h
+
+
+def pathnet_dw(dz: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None,
+               accumulate: bool = False) -> torch.Tensor:
+    """dW1 (256,in) fp32 (+)= dz^T x."""
+    _chk(dz, torch.bfloat16, "dz"); _chk(x, torch.bfloat16, "x")
+    rows, kin = x.shape
+    if out is None:
+        out = torch.empty(D, kin, device=x.device, dtype=torch.float32)
+        accumulate = False
+    ws = _workspace(_lib.query("imp_pathnet_dw_workspace_bytes", kin), x.device)
+    _lib.call("imp_pathnet_dw", dz, x, out, ws, rows, kin, bool(accumulate), _lib.stream_ptr())
+    return out
+
+
+def pool_fwd(h: torch.Tensor, cu_seqlens: torch.Tensor, max_len: int, qt: torch.Tensor
+             ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Softmax pooling of each bag's patches into P tokens.  qt (B,P,256) or (1,P,256)/(P,256)
+    shared.  Returns pooled (B,P,256) fp32, lse (B,P) fp32   [attention.py:509-530]."""
+    _chk(h, torch.bfloat16, "h"); _chk(cu_seqlens, torch.int32, "cu_seqlens"); _chk(qt, torch.float32, "qt")
+    nb = cu_seqlens.numel() - 1
+    if qt.dim() == 2:
+        qt = qt.unsqueeze(0)
+    p = qt.shape[1]
+    stride = 0 if qt.shape[0] == 1 and nb != 1 else p * D
+    if qt.shape[0] not in (1, nb):
+        raise ValueError("qt batch %d does not match %d bags" % (qt.shape[0], nb))
+    pooled = torch.empty(nb, p, D, device=h.device, dtype=torch.float32)
+    lse = torch.empty(nb, p, device=h.device, dtype=torch.float32)
+    ws = _workspace(_lib.query("imp_pool_fwd_workspace_bytes", nb, int(max_len), p), h.device)
+    _lib.call("imp_pool_fwd", h, h.shape[0], cu_seqlens, nb, int(max_len), qt, ctypes.c_longlong(stride), p,
+              ws, pooled, lse, _lib.stream_ptr())
+    return pooled, lse
+
+
+def pool_bwd(h: torch.Tensor, cu_seqlens: torch.Tensor, max_len: int, qt: Sequence[torch.Tensor],
+             dpooled: Sequence[torch.Tensor], lse: Sequence[torch.Tensor], delta: Sequence[torch.Tensor],
+             dq_block: int, want_dz: bool, relu_mask: bool = True, keep_scale: float = 1.0,
+             db1: Optional[torch.Tensor] = None, db_accumulate: bool = False):
+    """Backward of 1 or 2 stacked pooling blocks sharing h.  Returns (dq (B,P,256), dz or None)."""
+    nblk = len(qt)
+    nb = cu_seqlens.numel() - 1
+    _chk(h, torch.bfloat16, "h"); _chk(cu_seqlens, torch.int32, "cu_seqlens")
+    qs, strides = [], []
+    for k in range(nblk):
+        q = qt[k] if qt[k].dim() == 3 else qt[k].unsqueeze(0)
+        _chk(q, torch.float32, "qt"); _chk(dpooled[k], torch.float32, "dpooled")
+        _chk(lse[k], torch.float32, "lse"); _chk(delta[k], torch.float32, "delta")
+        qs.append(q)
+        strides.append(0 if q.shape[0] == 1 and nb != 1 else q.shape[1] * D)
+    p = qs[0].shape[1]
+    dq = torch.empty(nb, p, D, device=h.device, dtype=torch.float32)
+    dz = torch.empty_like(h) if want_dz else None
+    ws = _workspace(_lib.query("imp_pool_bwd_workspace_bytes", nb, int(max_len), p), h.device)
+    _lib.call("imp_pool_bwd", h, h.shape[0], cu_seqlens, nb, int(max_len), nblk, _ptr_array(qs),
+              (ctypes.c_longlong * nblk)(*strides), _ptr_array(list(dpooled)), _ptr_array(list(lse)),
+              _ptr_array(list(delta)), p, int(dq_block), bool(relu_mask), float(keep_scale), ws, dq, dz,
+              db1 if want_dz else None, bool(db_accumulate), _lib.stream_ptr())
+    return dq, dz
