@@ -64,6 +64,20 @@ int imp_pool_bwd(const void* h, int total_rows, const int* cu_seqlens, int n_bag
                  void* dz,
                  float* db1, int db_accumulate, void* stream);
 
+/* A0  sentinel strip: medmm/modeling/models/umeml_gan.py:401-410 (+ pad value data_manager.py:387).
+ * img (n_bags,n_pad,dim) fp32 in the reference batch layout; lengths[b] = index of the first row
+ * that holds an element equal to `sentinel` (-10000), or n_pad when there is none (the reference
+ * leaves that case undefined).  If cu_seqlens != NULL it receives the (n_bags+1) exclusive prefix
+ * sums, computed on the device (replaces the reference's per-slide .item() host sync). */
+int imp_bag_lengths(const float* img, int n_bags, int n_pad, int dim, float sentinel, int* lengths,
+                    int* cu_seqlens, void* stream);
+/* valid rows of img -> x_packed (cu_seqlens[n_bags], dim) bf16, bag b at rows [cu[b], cu[b+1]).
+ * x_packed must have room for n_bags*n_pad rows unless the caller knows the total. */
+int imp_pack_bags(const float* img, int n_bags, int n_pad, int dim, const int* cu_seqlens, void* x_packed,
+                  void* stream);
+/* fp32 -> bf16 round-to-nearest-even of n elements (n % 4 == 0); weights and packed features. */
+int imp_cast_bf16(const float* src, void* dst, size_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,3 +103,21 @@ extern "C" int imp_pool_bwd(const void* h, int total_rows, const int* cu_seqlens
                          lse, delta, n_proto, dq_block, relu_mask, keep_scale, (float*)workspace, dq, (bf16*)dz, db1,
                          db_accumulate, ST(stream));
 }
+
+// ------------------------------------------------------------------------------------------
+// A0 sentinel strip + wire-format conversion
+// ------------------------------------------------------------------------------------------
+extern "C" int imp_bag_lengths(const float* img, int n_bags, int n_pad, int dim, float sentinel, int* lengths,
+                               int* cu_seqlens, void* stream) {
+  if (!img || !lengths) IMP_FAIL(IMP_ERR_ARG, "imp_bag_lengths: null pointer");
+  return launch_bag_lengths(img, n_bags, n_pad, dim, sentinel, lengths, cu_seqlens, ST(stream));
+}
+extern "C" int imp_pack_bags(const float* img, int n_bags, int n_pad, int dim, const int* cu_seqlens, void* x_packed,
+                             void* stream) {
+  if (!img || !cu_seqlens || !x_packed) IMP_FAIL(IMP_ERR_ARG, "imp_pack_bags: null pointer");
+  return launch_pack_bags(img, n_bags, n_pad, dim, cu_seqlens, (bf16*)x_packed, ST(stream));
+}
+extern "C" int imp_cast_bf16(const float* src, void* dst, size_t n, void* stream) {
+  if (!src || !dst) IMP_FAIL(IMP_ERR_ARG, "imp_cast_bf16: null pointer");
+  return launch_cast_bf16(src, (bf16*)dst, n, ST(stream));
+}

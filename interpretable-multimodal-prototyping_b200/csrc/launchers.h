@@ -20,3 +20,8 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
                     const float* const* qt, const long long* qt_stride, const float* const* dpool,
                     const float* const* lse, const float* const* delta, int P, int dq_block, int relu_mask,
                     float keep_scale, float* workspace, float* dq, bf16* dz, float* db1, int db_accumulate, cudaStream_t st);
+
+// prep.cu
+int launch_bag_lengths(const float* img, int B, int npad, int d, float sentinel, int* lengths, int* cu, cudaStream_t st);
+int launch_pack_bags(const float* img, int B, int npad, int d, const int* cu, bf16* out, cudaStream_t st);
+int launch_cast_bf16(const float* src, bf16* dst, size_t n, cudaStream_t st);

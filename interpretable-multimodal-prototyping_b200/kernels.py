@@ -109,3 +109,34 @@ def pool_bwd(h: torch.Tensor, cu_seqlens: torch.Tensor, max_len: int, qt: Sequen
               _ptr_array(list(delta)), p, int(dq_block), bool(relu_mask), float(keep_scale), ws, dq, dz,
               db1 if want_dz else None, bool(db_accumulate), _lib.stream_ptr())
     return dq, dz
+
+
+def cast_bf16(t: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 (round to nearest even) on the device."""
+    _chk(t, torch.float32, "t")
+    out = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
+    n = t.numel()
+    if n % 4:
+        raise ValueError("cast_bf16: element count must be a multiple of 4")
+    if n:
+        _lib.call("imp_cast_bf16", t, out, ctypes.c_size_t(n), _lib.stream_ptr())
+    return out
+
+
+def bag_lengths(img: torch.Tensor, sentinel: float = -10000.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """img (B,Npad,D) fp32 -> (lengths (B) int32, cu_seqlens (B+1) int32), all on the device
+    [umeml_gan.py:401-410]."""
+    _chk(img, torch.float32, "img")
+    b, npad, d = img.shape
+    lengths = torch.empty(b, device=img.device, dtype=torch.int32)
+    cu = torch.empty(b + 1, device=img.device, dtype=torch.int32)
+    _lib.call("imp_bag_lengths", img, b, npad, d, float(sentinel), lengths, cu, _lib.stream_ptr())
+    return lengths, cu
+
+
+def pack_bags(img: torch.Tensor, cu_seqlens: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """valid rows of img (B,Npad,D) fp32 -> out (>= cu[B], D) bf16 packed."""
+    _chk(img, torch.float32, "img"); _chk(cu_seqlens, torch.int32, "cu_seqlens"); _chk(out, torch.bfloat16, "out")
+    b, npad, d = img.shape
+    _lib.call("imp_pack_bags", img, b, npad, d, cu_seqlens, out, _lib.stream_ptr())
+    return out

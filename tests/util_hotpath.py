@@ -1,0 +1,48 @@
+"""Shared synthetic-input builders for the parity tests (SURVEY.md 8(d) shapes)."""
+import math
+
+import torch
+
+PARAM_SHAPES = {
+    "path_net.0.weight": (256, 512), "path_net.0.bias": (256,),
+}
+for _b in range(2):
+    _p = "proto_g_blocks.%d." % _b
+    PARAM_SHAPES.update({
+        _p + "cross_attn.in_proj_weight": (768, 256), _p + "cross_attn.in_proj_bias": (768,),
+        _p + "cross_attn.out_proj.weight": (256, 256), _p + "cross_attn.out_proj.bias": (256,),
+        _p + "norm1.weight": (256,), _p + "norm1.bias": (256,),
+    })
+
+
+def make_params(seed=0, bias_scale=0.02):
+    """Reference initialisers (nn.Linear default, xavier_uniform in_proj) with non-zero biases so that
+    every gradient path is exercised."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, shp in PARAM_SHAPES.items():
+        if k.endswith("norm1.weight"):
+            out[k] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif len(shp) == 1:
+            out[k] = bias_scale * torch.randn(shp, generator=g)
+        else:
+            bound = math.sqrt(6.0 / (shp[0] + shp[1])) if "in_proj" in k else 1.0 / math.sqrt(shp[1])
+            out[k] = (torch.rand(shp, generator=g) * 2 - 1) * bound
+    return out
+
+
+def make_bags(lens, seed=0):
+    g = torch.Generator().manual_seed(seed + 100)
+    return [torch.randn(n, 512, generator=g) for n in lens]
+
+
+def block_tensors(params, b):
+    p = "proto_g_blocks.%d." % b
+    return [params[p + "cross_attn.in_proj_weight"], params[p + "cross_attn.in_proj_bias"],
+            params[p + "cross_attn.out_proj.weight"], params[p + "cross_attn.out_proj.bias"],
+            params[p + "norm1.weight"], params[p + "norm1.bias"]]
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
