@@ -78,6 +78,57 @@ int imp_pack_bags(const float* img, int n_bags, int n_pad, int dim, const int* c
 /* fp32 -> bf16 round-to-nearest-even of n elements (n % 4 == 0); weights and packed features. */
 int imp_cast_bf16(const float* src, void* dst, size_t n, void* stream);
 
+/* A4-A6  modularity loss and its gradient: medmm/modeling/ops/utils.py:178-228 (cluster_assignment_matrix,
+ * get_modularity_matrix_and_edge, compute_modularity), call sites umeml_gan.py:516-529.
+ * h (total_rows,256) bf16 packed bags (treated as detached, utils.py:208).  chat (n_bags, n_tok1+n_tok2, 256)
+ * fp32: the token matrices ALREADY normalised across tokens per feature (the F.normalize(dim=1) on c.T,
+ * utils.py:180,214, stays in the caller so autograd handles it); tokens [0,n_tok1) and
+ * [n_tok1,n_tok1+n_tok2) are two independent groups evaluated against the same patch graph
+ * (prototype tokens and omic tokens).  n_tok1 in [1,32], n_tok2 in [0,8].
+ * loss (n_bags,2) fp32 <- -100 tr((W/e) delta) per group (utils.py:222-228; 0 for an empty group);
+ * dchat (n_bags, n_tok1+n_tok2, 256) fp32 <- d loss_group / d chat. */
+size_t imp_modularity_workspace_bytes(int total_rows, int n_bags, int n_tok1, int n_tok2);
+int imp_modularity(const void* h, int total_rows, const int* cu_seqlens, int n_bags, int max_len,
+                   const float* chat, int n_tok1, int n_tok2, float temp, void* workspace, float* loss,
+                   float* dchat, void* stream);
+
+/* A7  per-pathway omic encoders: medmm/modeling/models/umeml_gan.py:274-283,413-419, with the
+ * feature-level imputation of :391-392 fused into the gather.
+ * x_omic (batch,n_genes) fp32; insample_mask (batch,n_genes) int32 or NULL (1 = gene missing, its
+ * value is replaced by omic_means[gene]); gene_index: concatenated column indices of the groups,
+ * group k at [group_offsets[k], group_offsets[k+1]) (group_offsets is a HOST array of n_groups+1 ints);
+ * weights[k] (256, G_k), biases[k] (256) fp32 (HOST arrays of device pointers, n_groups <= 8).
+ * out (batch, n_groups, 256) fp32 = Dropout_p(ReLU(x[:, idx_k] W_k^T + b_k)). */
+int imp_omic_encode_fwd(const float* x_omic, const int* insample_mask, const float* omic_means,
+                        const int* gene_index, const int* group_offsets, int n_groups,
+                        const float* const* weights, const float* const* biases, int batch, int n_genes,
+                        float p_drop, unsigned seed, float* out, void* stream);
+/* backward of A7 wrt the encoder weights/biases (inputs carry no gradient): dweights[k] (256,G_k),
+ * dbiases[k] (256) (+)= ...; `out` is the forward output (its zeros are the ReLU/dropout mask). */
+int imp_omic_encode_bwd(const float* x_omic, const int* insample_mask, const float* omic_means,
+                        const int* gene_index, const int* group_offsets, int n_groups, int batch, int n_genes,
+                        float p_drop, const float* out, const float* dout, float* const* dweights,
+                        float* const* dbiases, int accumulate, void* stream);
+/* A8  missing-omics handling of the omic tokens: umeml_gan.py:500-511.
+ *   h = where(without_omic[b] == 1, gen, h_omic)             (:503-505; without_omic (batch) int32 or NULL)
+ *   r = sum(insample_mask)/mask_numel over the whole batch   (:509; NULL mask -> r = 0)
+ *   out = (1-r) h + r gen                                    (:510-511)
+ * The reference's host-side "if sum(...) > 0" tests become device no-ops; scratch = 1 float;
+ * ratio_out (1 float, may be NULL) receives r.  h_omic, gen, out: (batch, per_sample) fp32. */
+int imp_omic_blend(const float* h_omic, const float* h_omic_gen, const int* without_omic,
+                   const int* insample_mask, long long mask_numel, int batch, int per_sample,
+                   float* scratch, float* out, float* ratio_out, void* stream);
+
+/* A9  k-means prototype assignment (NEW: the reference has no k-means; distance formula of
+ * medmm/metrics/distance.py:46-61 followed by argmin, first index on ties).
+ * x (n,dim) fp32, centroids (k,dim) fp32, k <= 64, dim % 32 == 0 -> assign (n) int32;
+ * best_dist (n) fp32 (may be NULL) <- the winning squared distance. */
+int imp_kmeans_assign(const float* x, const float* centroids, int n, int dim, int k, int* assign,
+                      float* best_dist, void* stream);
+/* Lloyd update: sums (k,dim) fp32 += x rows per assigned centroid, counts (k) int32 += 1 (caller zeroes). */
+int imp_kmeans_update(const float* x, const int* assign, int n, int dim, int k, float* sums, int* counts,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

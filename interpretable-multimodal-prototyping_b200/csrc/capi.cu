@@ -121,3 +121,58 @@ extern "C" int imp_cast_bf16(const float* src, void* dst, size_t n, void* stream
   if (!src || !dst) IMP_FAIL(IMP_ERR_ARG, "imp_cast_bf16: null pointer");
   return launch_cast_bf16(src, (bf16*)dst, n, ST(stream));
 }
+
+// ------------------------------------------------------------------------------------------
+// A4-A6 modularity loss + gradient wrt the normalised tokens
+// ------------------------------------------------------------------------------------------
+extern "C" size_t imp_modularity_workspace_bytes(int total_rows, int n_bags, int n_tok1, int n_tok2) {
+  return modularity_workspace_bytes(total_rows, n_bags, n_tok1, n_tok2);
+}
+extern "C" int imp_modularity(const void* h, int total_rows, const int* cu_seqlens, int n_bags, int max_len,
+                              const float* chat, int n_tok1, int n_tok2, float temp, void* workspace, float* loss,
+                              float* dchat, void* stream) {
+  if (!h || !cu_seqlens || !chat || !workspace || !loss || !dchat) IMP_FAIL(IMP_ERR_ARG, "imp_modularity: null pointer");
+  return launch_modularity((const bf16*)h, total_rows, cu_seqlens, n_bags, max_len, chat, n_tok1, n_tok2, temp,
+                           workspace, loss, dchat, ST(stream));
+}
+
+// ------------------------------------------------------------------------------------------
+// A7 per-pathway omic encoders, A8 missing-omics handling
+// ------------------------------------------------------------------------------------------
+extern "C" int imp_omic_encode_fwd(const float* x_omic, const int* insample_mask, const float* omic_means,
+                                   const int* gene_index, const int* group_offsets, int n_groups,
+                                   const float* const* weights, const float* const* biases, int batch, int n_genes,
+                                   float p_drop, unsigned seed, float* out, void* stream) {
+  if (!x_omic || !gene_index || !group_offsets || !weights || !biases || !out) IMP_FAIL(IMP_ERR_ARG, "imp_omic_encode_fwd: null pointer");
+  return launch_omic_fwd(x_omic, insample_mask, omic_means, gene_index, group_offsets, n_groups, weights, biases, batch,
+                         n_genes, p_drop, seed, out, ST(stream));
+}
+extern "C" int imp_omic_encode_bwd(const float* x_omic, const int* insample_mask, const float* omic_means,
+                                   const int* gene_index, const int* group_offsets, int n_groups, int batch, int n_genes,
+                                   float p_drop, const float* out, const float* dout, float* const* dweights,
+                                   float* const* dbiases, int accumulate, void* stream) {
+  if (!x_omic || !gene_index || !group_offsets || !out || !dout || !dweights || !dbiases) IMP_FAIL(IMP_ERR_ARG, "imp_omic_encode_bwd: null pointer");
+  return launch_omic_bwd(x_omic, insample_mask, omic_means, gene_index, group_offsets, n_groups, batch, n_genes, p_drop,
+                         out, dout, dweights, dbiases, accumulate, ST(stream));
+}
+extern "C" int imp_omic_blend(const float* h_omic, const float* h_omic_gen, const int* without_omic,
+                              const int* insample_mask, long long mask_numel, int batch, int per_sample,
+                              float* scratch, float* out, float* ratio_out, void* stream) {
+  if (!h_omic || !h_omic_gen || !out) IMP_FAIL(IMP_ERR_ARG, "imp_omic_blend: null pointer");
+  return launch_omic_blend(h_omic, h_omic_gen, without_omic, insample_mask, mask_numel, batch, per_sample, scratch, out,
+                           ratio_out, ST(stream));
+}
+
+// ------------------------------------------------------------------------------------------
+// A9 k-means prototype assignment / Lloyd update
+// ------------------------------------------------------------------------------------------
+extern "C" int imp_kmeans_assign(const float* x, const float* centroids, int n, int dim, int k, int* assign,
+                                 float* best_dist, void* stream) {
+  if (!x || !centroids || !assign) IMP_FAIL(IMP_ERR_ARG, "imp_kmeans_assign: null pointer");
+  return launch_kmeans_assign(x, centroids, n, dim, k, assign, best_dist, ST(stream));
+}
+extern "C" int imp_kmeans_update(const float* x, const int* assign, int n, int dim, int k, float* sums, int* counts,
+                                 void* stream) {
+  if (!x || !assign || !sums || !counts) IMP_FAIL(IMP_ERR_ARG, "imp_kmeans_update: null pointer");
+  return launch_kmeans_update(x, assign, n, dim, k, sums, counts, ST(stream));
+}

@@ -25,3 +25,25 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
 int launch_bag_lengths(const float* img, int B, int npad, int d, float sentinel, int* lengths, int* cu, cudaStream_t st);
 int launch_pack_bags(const float* img, int B, int npad, int d, const int* cu, bf16* out, cudaStream_t st);
 int launch_cast_bf16(const float* src, bf16* dst, size_t n, cudaStream_t st);
+
+// modularity.cu
+size_t modularity_workspace_bytes(int total_rows, int B, int P1, int P2);
+int launch_modularity(const bf16* h, int total_rows, const int* cu, int B, int max_len, const float* chat, int P1, int P2,
+                      float temp, void* workspace, float* loss, float* dchat, cudaStream_t st);
+
+// omic.cu
+int launch_omic_fwd(const float* x, const int* mask, const float* means, const int* idx, const int* group_offsets,
+                    int K, const float* const* w, const float* const* bias, int B, int G, float p_drop, unsigned seed,
+                    float* out, cudaStream_t st);
+int launch_omic_bwd(const float* x, const int* mask, const float* means, const int* idx, const int* group_offsets,
+                    int K, int B, int G, float p_drop, const float* out, const float* dout, float* const* dw,
+                    float* const* db, int accumulate, cudaStream_t st);
+int launch_omic_blend(const float* h_omic, const float* h_gen, const int* without_omic, const int* insample_mask,
+                      long long mask_numel, int B, int per_sample, float* scratch, float* out, float* ratio_out,
+                      cudaStream_t st);
+
+// kmeans.cu
+int launch_kmeans_assign(const float* x, const float* mu, int N, int D, int K, int* assign, float* best_dist,
+                         cudaStream_t st);
+int launch_kmeans_update(const float* x, const int* assign, int N, int D, int K, float* sums, int* counts,
+                         cudaStream_t st);

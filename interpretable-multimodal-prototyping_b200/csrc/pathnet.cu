@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
 pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   float* s_bias = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kDwThreads, 1)
 pathnet_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_x,
                   const DwParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kDwStages * kDwStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kDwStages;

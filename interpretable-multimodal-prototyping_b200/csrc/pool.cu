@@ -35,9 +35,8 @@ __device__ __forceinline__ uint32_t gmat_off(int row, int col) {
 __device__ __forceinline__ void bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
-__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
-  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
-}
+// pointer arithmetic (not an integer round trip) so the compiler keeps the shared address space
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
 
 // rows [0,nvalid) of src (fp32, row stride 256) -> bf16 swizzled rows [row0,row0+nrows) of dst; rest zero
 __device__ __forceinline__ void load_gmat_rows(uint8_t* dst, int row0, int nrows, const float* src, int nvalid,

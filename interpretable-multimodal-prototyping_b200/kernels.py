@@ -140,3 +140,76 @@ def pack_bags(img: torch.Tensor, cu_seqlens: torch.Tensor, out: torch.Tensor) ->
     b, npad, d = img.shape
     _lib.call("imp_pack_bags", img, b, npad, d, cu_seqlens, out, _lib.stream_ptr())
     return out
+
+
+def modularity(h: torch.Tensor, cu_seqlens: torch.Tensor, max_len: int, chat: torch.Tensor, n_tok1: int,
+               n_tok2: int = 0, temp: float = 0.1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Modularity loss per (bag, token group) and its gradient wrt the normalised tokens
+    [ops/utils.py:178-228].  chat (B, n_tok1+n_tok2, 256) fp32 -> (loss (B,2), dchat like chat)."""
+    _chk(h, torch.bfloat16, "h"); _chk(cu_seqlens, torch.int32, "cu_seqlens"); _chk(chat, torch.float32, "chat")
+    nb = cu_seqlens.numel() - 1
+    if chat.shape != (nb, n_tok1 + n_tok2, D):
+        raise ValueError("chat shape %s != (%d,%d,%d)" % (tuple(chat.shape), nb, n_tok1 + n_tok2, D))
+    loss = torch.empty(nb, 2, device=h.device, dtype=torch.float32)
+    dchat = torch.empty_like(chat)
+    nbytes = _lib.query("imp_modularity_workspace_bytes", h.shape[0], nb, n_tok1, n_tok2)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=h.device)       # 256-byte aligned by the allocator
+    _lib.call("imp_modularity", h, h.shape[0], cu_seqlens, nb, int(max_len), chat, int(n_tok1), int(n_tok2),
+              float(temp), ws, loss, dchat, _lib.stream_ptr())
+    return loss, dchat
+
+
+def _int_array(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def omic_encode_fwd(x_omic: torch.Tensor, gene_index: torch.Tensor, group_offsets: Sequence[int],
+                    weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
+                    insample_mask: Optional[torch.Tensor] = None, omic_means: Optional[torch.Tensor] = None,
+                    p_drop: float = 0.0, seed: int = 0) -> torch.Tensor:
+    """(B,G) fp32 -> (B,K,256) fp32   [umeml_gan.py:274-283,391-392,413-419]."""
+    _chk(x_omic, torch.float32, "x_omic"); _chk(gene_index, torch.int32, "gene_index")
+    if insample_mask is not None:
+        _chk(insample_mask, torch.int32, "insample_mask"); _chk(omic_means, torch.float32, "omic_means")
+    for w, b in zip(weights, biases):
+        _chk(w, torch.float32, "weight"); _chk(b, torch.float32, "bias")
+    bsz, g = x_omic.shape
+    k = len(weights)
+    out = torch.empty(bsz, k, D, device=x_omic.device, dtype=torch.float32)
+    _lib.call("imp_omic_encode_fwd", x_omic, insample_mask, omic_means if insample_mask is not None else None,
+              gene_index, _int_array(group_offsets), k, _ptr_array(list(weights)), _ptr_array(list(biases)), bsz, g,
+              float(p_drop), int(seed) & 0x7FFFFFFF, out, _lib.stream_ptr())
+    return out
+
+
+def omic_encode_bwd(x_omic, gene_index, group_offsets, out, dout, weights_like: Sequence[torch.Tensor],
+                    insample_mask=None, omic_means=None, p_drop: float = 0.0):
+    """-> (list of dW_k (256,G_k), list of db_k (256))."""
+    _chk(out, torch.float32, "out"); _chk(dout, torch.float32, "dout")
+    bsz, g = x_omic.shape
+    k = len(weights_like)
+    dws = [torch.empty_like(w) for w in weights_like]
+    dbs = [torch.empty(D, device=x_omic.device, dtype=torch.float32) for _ in range(k)]
+    _lib.call("imp_omic_encode_bwd", x_omic, insample_mask, omic_means if insample_mask is not None else None,
+              gene_index, _int_array(group_offsets), k, bsz, g, float(p_drop), out, dout, _ptr_array(dws),
+              _ptr_array(dbs), False, _lib.stream_ptr())
+    return dws, dbs
+
+
+def omic_blend(h_omic: torch.Tensor, h_gen: torch.Tensor, without_omic: Optional[torch.Tensor] = None,
+               insample_mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Sample-level replacement + batch-ratio blend of the omic tokens [umeml_gan.py:500-511].
+    Returns (blended tokens, r (1) fp32)."""
+    _chk(h_omic, torch.float32, "h_omic"); _chk(h_gen, torch.float32, "h_gen")
+    if without_omic is not None:
+        _chk(without_omic, torch.int32, "without_omic")
+    if insample_mask is not None:
+        _chk(insample_mask, torch.int32, "insample_mask")
+    bsz = h_omic.shape[0]
+    per = h_omic.numel() // bsz
+    out = torch.empty_like(h_omic)
+    scratch = torch.empty(2, device=h_omic.device, dtype=torch.float32)
+    _lib.call("imp_omic_blend", h_omic, h_gen, without_omic, insample_mask,
+              ctypes.c_longlong(insample_mask.numel() if insample_mask is not None else 0), bsz, per,
+              scratch[0:1], out, scratch[1:2], _lib.stream_ptr())
+    return out, scratch[1:2]

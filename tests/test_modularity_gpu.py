@@ -1,0 +1,54 @@
+"""A4-A6 modularity kernels vs the CPU oracle (chunked fp64 restatement of ops/utils.py:178-228)
+on the same bf16-rounded patch tokens.  Tolerance 1e-3 relative (north_star) on the loss and,
+as relative Frobenius error, on the gradient wrt the tokens."""
+import pytest
+import torch
+
+from util_hotpath import rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(n, p, q, seed):
+    g = torch.Generator().manual_seed(seed)
+    base = torch.randn(8, 256, generator=g)
+    mix = torch.rand(n, 8, generator=g) ** 3
+    h = torch.relu(mix @ base + 0.3 * torch.randn(n, 256, generator=g)).bfloat16()
+    c1 = torch.randn(p, 256, generator=g)
+    c2 = torch.randn(q, 256, generator=g) if q else None
+    return h, c1, c2
+
+
+@pytest.mark.parametrize("n,p,q", [(128, 6, 0), (300, 16, 7), (1000, 6, 7), (2048, 32, 7), (4096 + 77, 32, 0)])
+def test_modularity_vs_oracle(n, p, q):
+    from imp_b200 import modularity as M
+    from oracle import imp_oracle as O
+    h, c1, c2 = _inputs(n, p, q, n)
+    cu = torch.tensor([0, n], dtype=torch.int32, device="cuda")
+    c1d = c1.cuda().unsqueeze(0).requires_grad_(True)
+    c2d = c2.cuda().unsqueeze(0).requires_grad_(True) if q else None
+    loss = M.modularity_terms(h.cuda(), cu, n, c1d, c2d)
+    (loss[0, 0] * 1.0 + loss[0, 1] * 2.0).backward()
+    torch.cuda.synchronize()
+    ref1, dref1 = O.modularity(c1, h.float(), chunk=256)
+    assert abs(loss[0, 0].item() - ref1.item()) <= 1e-3 * abs(ref1.item()) + 1e-5, (loss[0, 0].item(), ref1.item())
+    assert rel(c1d.grad[0], dref1) < 2e-3, rel(c1d.grad[0], dref1)
+    if q:
+        ref2, dref2 = O.modularity(c2, h.float(), chunk=256)
+        assert abs(loss[0, 1].item() - ref2.item()) <= 1e-3 * abs(ref2.item()) + 1e-5
+        assert rel(c2d.grad[0], 2.0 * dref2) < 2e-3, rel(c2d.grad[0], 2.0 * dref2)
+
+
+def test_modularity_batched_varlen_matches_single():
+    from imp_b200 import modularity as M
+    lens = [257, 640, 130]
+    hs, cs = [], []
+    for i, n in enumerate(lens):
+        h, c1, _ = _inputs(n, 16, 0, 50 + i)
+        hs.append(h); cs.append(c1)
+    hcat = torch.cat(hs).cuda()
+    cu = torch.tensor([0, 257, 897, 1027], dtype=torch.int32, device="cuda")
+    batched = M.modularity_terms(hcat, cu, max(lens), torch.stack(cs).cuda())
+    for i, n in enumerate(lens):
+        single = M.compute_modularity(cs[i].cuda().unsqueeze(0), hs[i].cuda().float().unsqueeze(0))
+        assert abs(batched[i, 0].item() - single.item()) <= 1e-4 * abs(single.item()) + 1e-6
