@@ -25,6 +25,14 @@ extern "C" {
 const char* imp_last_error(void);
 int imp_abi_version(void);
 
+/* Launch accounting (measurement only).  imp_launch_count: kernels launched by this library so far.
+ * imp_profile_enable(1): bracket every launch with CUDA events on its stream; imp_profile_collect
+ * synchronises the device and returns (kernel name, milliseconds) for the launches since the last
+ * collect (HOST arrays, up to max_records; returns the count, -1 on a CUDA error). */
+long long imp_launch_count(void);
+int imp_profile_enable(int on);
+int imp_profile_collect(const char** names, float* ms, int max_records);
+
 /* A1  path_net: h = Dropout_p(ReLU(x W1^T + b1))        medmm/modeling/models/umeml_gan.py:266-268,410
  * x (rows,in_features) bf16 row-major, w1 (256,in_features) bf16, b1 (256) fp32 -> h (rows,256) bf16.
  * The dropout keep-mask is a stateless hash of (seed,row,col); the same seed regenerates it. */

@@ -5,4 +5,4 @@ hand-written CUDA in ``csrc/`` behind the C-ABI of ``include/imp_hotpath.h``.  N
 """
 from . import _lib  # noqa: F401
 
-__all__ = ["_lib"]
+__all__ = ["_lib", "kernels", "ops", "modularity", "omics", "model", "prototypes", "step", "parallel"]

@@ -69,3 +69,23 @@ def query(name: str, *args) -> int:
 def stream_ptr():
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    fn = lib().imp_launch_count
+    fn.restype = ctypes.c_longlong
+    return int(fn())
+
+
+def profile_enable(on: bool) -> None:
+    lib().imp_profile_enable(ctypes.c_int(1 if on else 0))
+
+
+def profile_collect(max_records: int = 65536):
+    """-> list of (kernel name, ms) for the launches recorded since the last collect."""
+    names = (ctypes.c_char_p * max_records)()
+    ms = (ctypes.c_float * max_records)()
+    n = lib().imp_profile_collect(names, ms, ctypes.c_int(max_records))
+    if n < 0:
+        raise ImpError("imp_profile_collect: CUDA error")
+    return [(names[i].decode(), float(ms[i])) for i in range(n)]

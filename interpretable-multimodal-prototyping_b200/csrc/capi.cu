@@ -60,6 +60,65 @@ int imp_num_sms() {
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
 // ------------------------------------------------------------------------------------------
+// launch accounting: a counter of kernel launches and an optional per-launch CUDA-event timer
+// ------------------------------------------------------------------------------------------
+#include <atomic>
+#include <mutex>
+#include <vector>
+namespace {
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_prof_on{0};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof_recs;       // recorded launches, in order
+std::vector<ProfRec> g_prof_pool;       // reusable event pairs
+thread_local ProfRec g_prof_cur = {nullptr, nullptr, nullptr};
+}  // namespace
+
+void imp_prof_begin(const char* name, cudaStream_t st) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  g_prof_cur.name = nullptr;
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec r{name, nullptr, nullptr};
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_pool.empty()) { r = g_prof_pool.back(); g_prof_pool.pop_back(); r.name = name; }
+  }
+  if (!r.a && (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess)) return;
+  cudaEventRecord(r.a, st);
+  g_prof_cur = r;
+}
+void imp_prof_end(cudaStream_t st) {
+  if (!g_prof_cur.name) return;
+  cudaEventRecord(g_prof_cur.b, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_recs.push_back(g_prof_cur);
+  g_prof_cur.name = nullptr;
+}
+
+extern "C" long long imp_launch_count(void) { return g_launches.load(); }
+extern "C" int imp_profile_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+  return IMP_OK;
+}
+// Synchronises the device, then writes up to `max_records` (name, milliseconds) pairs of the launches
+// recorded since the last collect; returns the number written (records beyond max are dropped).
+extern "C" int imp_profile_collect(const char** names, float* ms, int max_records) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int n = 0;
+  for (ProfRec& r : g_prof_recs) {
+    if (n < max_records) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { names[n] = r.name; ms[n] = t; ++n; }
+    }
+    g_prof_pool.push_back(r);
+  }
+  g_prof_recs.clear();
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
 // A1 path_net
 // ------------------------------------------------------------------------------------------
 extern "C" int imp_pathnet_fwd(const void* x, const void* w1, const float* b1, void* h, int rows, int in_features,

@@ -31,6 +31,17 @@ extern thread_local char g_imp_err[512];
                cudaGetErrorString(_e));                                                 \
   } while (0)
 #define IMP_LAUNCH_CHECK() IMP_CUDA(cudaGetLastError())
+// every kernel launch goes through IMP_LAUNCH: counts it and, when profiling is on, brackets it
+// with CUDA events on the launching stream (imp_profile_enable / imp_profile_collect)
+void imp_prof_begin(const char* name, cudaStream_t st);
+void imp_prof_end(cudaStream_t st);
+#define IMP_LAUNCH(name, st, ...)   \
+  do {                              \
+    imp_prof_begin(name, st);       \
+    __VA_ARGS__;                    \
+    imp_prof_end(st);               \
+    IMP_LAUNCH_CHECK();             \
+  } while (0)
 
 // host: encode a 2-D row-major tensor map (inner dim contiguous)
 int imp_make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elt_bytes,

@@ -158,8 +158,7 @@ int run_assign(const CUtensorMap& tm, const KmParams& p, cudaStream_t st) {
     attr = smem;
   }
   const int grid = std::min(p.num_tiles, imp_num_sms());
-  kmeans_assign_kernel<KP><<<grid, kThreads, smem, st>>>(tm, p);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("kmeans_assign", st, kmeans_assign_kernel<KP><<<grid, kThreads, smem, st>>>(tm, p));
   return IMP_OK;
 }
 
@@ -195,7 +194,6 @@ int launch_kmeans_update(const float* x, const int* assign, int N, int D, int K,
     attr = smem;
   }
   const int grid = std::min((N + 63) / 64, 2 * imp_num_sms());
-  kmeans_update_kernel<<<grid, 256, smem, st>>>(x, assign, sums, counts, N, D, K);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("kmeans_update", st, kmeans_update_kernel<<<grid, 256, smem, st>>>(x, assign, sums, counts, N, D, K));
   return IMP_OK;
 }

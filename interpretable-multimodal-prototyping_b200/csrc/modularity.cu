@@ -432,8 +432,7 @@ int run_gram(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p, 
     IMP_CUDA(cudaFuncSetAttribute(modularity_gram_kernel<MODE, NQ1, NQ2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done = true;
   }
-  modularity_gram_kernel<MODE, NQ1, NQ2><<<grid, kThreads, smem, st>>>(ta, tb, p);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH(MODE ? "modularity_gram_main" : "modularity_gram_degrees", st, modularity_gram_kernel<MODE, NQ1, NQ2><<<grid, kThreads, smem, st>>>(ta, tb, p));
   return IMP_OK;
 }
 
@@ -493,8 +492,7 @@ int launch_modularity(const bf16* h, int total_rows, const int* cu, int B, int m
     prep_attr = true;
   }
   const int prep_chunks = std::max(1, std::min((max_len + 7) / 8, (4 * imp_num_sms() + B - 1) / B));
-  modularity_prep_kernel<<<dim3(prep_chunks, B), 256, prep_smem, st>>>(pp);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("modularity_prep", st, modularity_prep_kernel<<<dim3(prep_chunks, B), 256, prep_smem, st>>>(pp));
 
   CUtensorMap ta, tb;
   int rc;
@@ -525,11 +523,11 @@ int launch_modularity(const bf16* h, int total_rows, const int* cu, int B, int m
   fp.rows_per_cta = ((max_len + fin_chunks - 1) / fin_chunks + 31) & ~31;
   const dim3 fgrid((max_len + fp.rows_per_cta - 1) / fp.rows_per_cta, B);
   switch (PtPad) {
-    case 8: modularity_finish_kernel<8><<<fgrid, 256, 0, st>>>(fp); break;
-    case 16: modularity_finish_kernel<16><<<fgrid, 256, 0, st>>>(fp); break;
-    case 24: modularity_finish_kernel<24><<<fgrid, 256, 0, st>>>(fp); break;
-    case 32: modularity_finish_kernel<32><<<fgrid, 256, 0, st>>>(fp); break;
-    case 40: modularity_finish_kernel<40><<<fgrid, 256, 0, st>>>(fp); break;
+    case 8: IMP_LAUNCH("modularity_finish", st, modularity_finish_kernel<8><<<fgrid, 256, 0, st>>>(fp)); break;
+    case 16: IMP_LAUNCH("modularity_finish", st, modularity_finish_kernel<16><<<fgrid, 256, 0, st>>>(fp)); break;
+    case 24: IMP_LAUNCH("modularity_finish", st, modularity_finish_kernel<24><<<fgrid, 256, 0, st>>>(fp)); break;
+    case 32: IMP_LAUNCH("modularity_finish", st, modularity_finish_kernel<32><<<fgrid, 256, 0, st>>>(fp)); break;
+    case 40: IMP_LAUNCH("modularity_finish", st, modularity_finish_kernel<40><<<fgrid, 256, 0, st>>>(fp)); break;
     default: IMP_FAIL(IMP_ERR_ARG, "modularity: unsupported padded token count %d", PtPad);
   }
   IMP_LAUNCH_CHECK();

@@ -193,8 +193,7 @@ int launch_omic_fwd(const float* x, const int* mask, const float* means, const i
     IMP_CUDA(cudaFuncSetAttribute(omic_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  omic_fwd_kernel<<<dim3(kD / 8, K, (B + kBB - 1) / kBB), 256, smem, st>>>(p);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("omic_fwd", st, omic_fwd_kernel<<<dim3(kD / 8, K, (B + kBB - 1) / kBB), 256, smem, st>>>(p));
   return IMP_OK;
 }
 
@@ -207,8 +206,7 @@ int launch_omic_bwd(const float* x, const int* mask, const float* means, const i
   int gmax = 0;
   for (int k = 0; k < K; ++k) { p.dw[k] = dw[k]; p.db[k] = db[k]; gmax = std::max(gmax, p.f.goff[k + 1] - p.f.goff[k]); }
   p.out = out; p.dout = dout; p.accumulate = accumulate;
-  omic_bwd_kernel<<<dim3((gmax + 31) / 32, K), 256, 0, st>>>(p);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("omic_bwd", st, omic_bwd_kernel<<<dim3((gmax + 31) / 32, K), 256, 0, st>>>(p));
   return IMP_OK;
 }
 
@@ -222,13 +220,11 @@ int launch_omic_blend(const float* h_omic, const float* h_gen, const int* withou
     ratio_sum = scratch;
     IMP_CUDA(cudaMemsetAsync(ratio_sum, 0, sizeof(float), st));
     const int blocks = (int)std::min<long long>((mask_numel + 255) / 256, (long long)imp_num_sms() * 4);
-    mask_ratio_kernel<<<blocks, 256, 0, st>>>(insample_mask, mask_numel, ratio_sum);
-    IMP_LAUNCH_CHECK();
+    IMP_LAUNCH("mask_ratio", st, mask_ratio_kernel<<<blocks, 256, 0, st>>>(insample_mask, mask_numel, ratio_sum));
   }
   const long long n = (long long)B * per_sample;
   const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)imp_num_sms() * 4);
-  omic_blend_kernel<<<blocks, 256, 0, st>>>(h_omic, h_gen, without_omic, ratio_sum,
-                                            mask_numel > 0 ? 1.f / (float)mask_numel : 0.f, out, ratio_out, B, per_sample);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("omic_blend", st, omic_blend_kernel<<<blocks, 256, 0, st>>>(h_omic, h_gen, without_omic, ratio_sum,
+                                            mask_numel > 0 ? 1.f / (float)mask_numel : 0.f, out, ratio_out, B, per_sample));
   return IMP_OK;
 }

@@ -324,8 +324,7 @@ int launch_pathnet_fwd(const bf16* x, const bf16* w1, const float* b1, bf16* h, 
     attr_done = true;
   }
   int grid = min(p.num_tiles, imp_num_sms());
-  pathnet_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(tm_x, tm_w, p);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("pathnet_fwd", st, pathnet_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(tm_x, tm_w, p));
   return IMP_OK;
 }
 
@@ -333,8 +332,7 @@ int launch_sum_partials(const float* partial, float* out, int nsplit, size_t n, 
                         cudaStream_t st) {
   if (n % 4) IMP_FAIL(IMP_ERR_ARG, "sum_partials: n must be a multiple of 4");
   size_t threads = n / 4;
-  sum_partials_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(partial, out, nsplit, n, scale, accumulate);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("sum_partials", st, sum_partials_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(partial, out, nsplit, n, scale, accumulate));
   return IMP_OK;
 }
 
@@ -368,7 +366,6 @@ int launch_pathnet_dw(const bf16* dz, const bf16* x, float* dw, float* workspace
     IMP_CUDA(cudaFuncSetAttribute(pathnet_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem));
     attr_done = true;
   }
-  pathnet_dw_kernel<<<p.ksplit * ntile, kDwThreads, kDwSmem, st>>>(tm_dz, tm_x, p);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("pathnet_dw", st, pathnet_dw_kernel<<<p.ksplit * ntile, kDwThreads, kDwSmem, st>>>(tm_dz, tm_x, p));
   return launch_sum_partials(workspace, dw, p.ksplit, (size_t)kD * kin, 1.f, accumulate, st);
 }

@@ -558,8 +558,7 @@ int run_fwd(const CUtensorMap& tm, const PoolFwdParams& p, int B, cudaStream_t s
     IMP_CUDA(cudaFuncSetAttribute(pool_fwd_kernel<PP, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done = true;
   }
-  pool_fwd_kernel<PP, STAGES><<<dim3(p.nsplit, B), kThreads, smem, st>>>(tm, p);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("pool_fwd", st, pool_fwd_kernel<PP, STAGES><<<dim3(p.nsplit, B), kThreads, smem, st>>>(tm, p));
   return IMP_OK;
 }
 template <int PP, int NB, bool DZ, int STAGES>
@@ -571,8 +570,7 @@ int run_bwd(const CUtensorMap& tm, const PoolBwdParams& p, int B, cudaStream_t s
     IMP_CUDA(cudaFuncSetAttribute(pool_bwd_kernel<PP, NB, DZ, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done = true;
   }
-  pool_bwd_kernel<PP, NB, DZ, STAGES><<<dim3(p.nsplit, B), kThreads, smem, st>>>(tm, p);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH(DZ ? "pool_bwd_dz" : "pool_bwd_dq", st, pool_bwd_kernel<PP, NB, DZ, STAGES><<<dim3(p.nsplit, B), kThreads, smem, st>>>(tm, p));
   return IMP_OK;
 }
 
@@ -607,8 +605,7 @@ int launch_pool_fwd(const bf16* h, int total_rows, const int* cu, int B, int max
   else if (PP == 32) rc = run_fwd<32, 4>(tm, p, B, st);
   else rc = run_fwd<64, 4>(tm, p, B, st);
   if (rc) return rc;
-  pool_merge_kernel<<<dim3(P, B), kD, 0, st>>>(p.part_acc, p.part_ml, pooled, lse, P, PP, p.nsplit);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("pool_merge", st, pool_merge_kernel<<<dim3(P, B), kD, 0, st>>>(p.part_acc, p.part_ml, pooled, lse, P, PP, p.nsplit));
   return IMP_OK;
 }
 
@@ -659,11 +656,9 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
   }
 #undef IMP_BWD
   if (rc) return rc;
-  reduce_dq_kernel<<<dim3(P, B), kD, 0, st>>>(p.part_dq, dq, P, PP, p.nsplit);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("reduce_dq", st, reduce_dq_kernel<<<dim3(P, B), kD, 0, st>>>(p.part_dq, dq, P, PP, p.nsplit));
   if (p.part_db) {
-    reduce_db_kernel<<<1, kD, 0, st>>>(p.part_db, db1, B * p.nsplit, db_accumulate);
-    IMP_LAUNCH_CHECK();
+    IMP_LAUNCH("reduce_db", st, reduce_db_kernel<<<1, kD, 0, st>>>(p.part_db, db1, B * p.nsplit, db_accumulate));
   }
   return IMP_OK;
 }

@@ -83,15 +83,12 @@ int launch_bag_lengths(const float* img, int B, int npad, int d, float sentinel,
   if (B <= 0 || npad <= 0 || d <= 0) IMP_FAIL(IMP_ERR_ARG, "bag_lengths: bad shape (%d,%d,%d)", B, npad, d);
   if (d % 4 != 0) IMP_FAIL(IMP_ERR_ARG, "bag_lengths: feature dim %d must be a multiple of 4", d);
   if ((long long)B * npad >= (1LL << 31)) IMP_FAIL(IMP_ERR_ARG, "bag_lengths: %lld rows exceed int32 offsets", (long long)B * npad);
-  init_lengths_kernel<<<(B + 255) / 256, 256, 0, st>>>(lengths, B, npad);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("init_lengths", st, init_lengths_kernel<<<(B + 255) / 256, 256, 0, st>>>(lengths, B, npad));
   const long long rows = (long long)B * npad;
   const int blocks = (int)std::min<long long>((rows + 7) / 8, (long long)imp_num_sms() * 16);
-  bag_lengths_kernel<<<blocks, 256, 0, st>>>(img, lengths, rows, npad, d, sentinel);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("bag_lengths", st, bag_lengths_kernel<<<blocks, 256, 0, st>>>(img, lengths, rows, npad, d, sentinel));
   if (cu) {
-    cu_seqlens_kernel<<<1, 1024, 0, st>>>(lengths, cu, B);
-    IMP_LAUNCH_CHECK();
+    IMP_LAUNCH("cu_seqlens", st, cu_seqlens_kernel<<<1, 1024, 0, st>>>(lengths, cu, B));
   }
   return IMP_OK;
 }
@@ -99,8 +96,7 @@ int launch_bag_lengths(const float* img, int B, int npad, int d, float sentinel,
 int launch_pack_bags(const float* img, int B, int npad, int d, const int* cu, bf16* out, cudaStream_t st) {
   if (B <= 0 || npad <= 0 || d <= 0 || d % 4 != 0) IMP_FAIL(IMP_ERR_ARG, "pack_bags: bad shape (%d,%d,%d)", B, npad, d);
   const int chunks = max(1, min(64, (2 * imp_num_sms() * 4 + B - 1) / B));
-  pack_bags_kernel<<<dim3(chunks, B), 256, 0, st>>>(img, cu, out, npad, d);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("pack_bags", st, pack_bags_kernel<<<dim3(chunks, B), 256, 0, st>>>(img, cu, out, npad, d));
   return IMP_OK;
 }
 
@@ -109,7 +105,6 @@ int launch_cast_bf16(const float* src, bf16* dst, size_t n, cudaStream_t st) {
   if (n == 0) return IMP_OK;
   const size_t n4 = n / 4;
   const int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)imp_num_sms() * 16);
-  cast_bf16_kernel<<<blocks, 256, 0, st>>>(src, dst, n4);
-  IMP_LAUNCH_CHECK();
+  IMP_LAUNCH("cast_bf16", st, cast_bf16_kernel<<<blocks, 256, 0, st>>>(src, dst, n4));
   return IMP_OK;
 }

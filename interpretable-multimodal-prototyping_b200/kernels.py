@@ -213,3 +213,24 @@ def omic_blend(h_omic: torch.Tensor, h_gen: torch.Tensor, without_omic: Optional
               ctypes.c_longlong(insample_mask.numel() if insample_mask is not None else 0), bsz, per,
               scratch[0:1], out, scratch[1:2], _lib.stream_ptr())
     return out, scratch[1:2]
+
+
+def kmeans_assign(x: torch.Tensor, centroids: torch.Tensor, want_dist: bool = False):
+    """argmin_k ||x_n - mu_k||^2 (first index on ties) -> int32 (N)   [metrics/distance.py:46-61 + argmin]."""
+    _chk(x, torch.float32, "x"); _chk(centroids, torch.float32, "centroids")
+    n, d = x.shape
+    k = centroids.shape[0]
+    assign = torch.empty(n, device=x.device, dtype=torch.int32)
+    dist = torch.empty(n, device=x.device, dtype=torch.float32) if want_dist else None
+    _lib.call("imp_kmeans_assign", x, centroids, n, d, k, assign, dist, _lib.stream_ptr())
+    return (assign, dist) if want_dist else assign
+
+
+def kmeans_update(x: torch.Tensor, assign: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-centroid sums (k,D) fp32 and counts (k) int32 of the assigned rows."""
+    _chk(x, torch.float32, "x"); _chk(assign, torch.int32, "assign")
+    n, d = x.shape
+    sums = torch.zeros(k, d, device=x.device, dtype=torch.float32)
+    counts = torch.zeros(k, device=x.device, dtype=torch.int32)
+    _lib.call("imp_kmeans_update", x, assign, n, d, int(k), sums, counts, _lib.stream_ptr())
+    return sums, counts

@@ -46,3 +46,16 @@ def block_tensors(params, b):
 def rel(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+GROUP_SIZES = [82, 330, 513, 440, 1538, 451]
+
+
+def make_omic_params(seed=0):
+    """omic_net.{k}.0.{weight,bias} (umeml_gan.py:274-283), deterministic from the seed."""
+    g = torch.Generator().manual_seed(seed + 777)
+    out = {}
+    for k, s in enumerate(GROUP_SIZES):
+        out["omic_net.%d.0.weight" % k] = (torch.rand(256, s, generator=g) * 2 - 1) / math.sqrt(s)
+        out["omic_net.%d.0.bias" % k] = 0.05 * torch.randn(256, generator=g)
+    return out
