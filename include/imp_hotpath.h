@@ -137,6 +137,13 @@ int imp_kmeans_assign(const float* x, const float* centroids, int n, int dim, in
 int imp_kmeans_update(const float* x, const int* assign, int n, int dim, int k, float* sums, int* counts,
                       void* stream);
 
+/* Multi-GPU giant bag: log-sum-exp merge of per-shard pooling results.  Each of the
+ * n_parts shards of a bag produced (pooled_r, lse_r) with imp_pool_fwd over its patches;
+ * part_pooled (n_bags, n_parts, P, 256), part_lse (n_bags, n_parts, P) (an empty shard has lse = -inf)
+ * -> pooled (n_bags,P,256), lse (n_bags,P) of the whole bag.  scratch: n_bags*n_parts*2*P floats. */
+int imp_lse_merge(const float* part_pooled, const float* part_lse, int n_bags, int n_parts, int n_proto,
+                  float* pooled, float* lse, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -235,3 +235,9 @@ extern "C" int imp_kmeans_update(const float* x, const int* assign, int n, int d
   if (!x || !assign || !sums || !counts) IMP_FAIL(IMP_ERR_ARG, "imp_kmeans_update: null pointer");
   return launch_kmeans_update(x, assign, n, dim, k, sums, counts, ST(stream));
 }
+
+extern "C" int imp_lse_merge(const float* part_pooled, const float* part_lse, int n_bags, int n_parts, int n_proto,
+                             float* pooled, float* lse, float* scratch, void* stream) {
+  if (!part_pooled || !part_lse || !pooled || !lse || !scratch) IMP_FAIL(IMP_ERR_ARG, "imp_lse_merge: null pointer");
+  return launch_lse_merge(part_pooled, part_lse, n_bags, n_parts, n_proto, pooled, lse, scratch, ST(stream));
+}

@@ -47,3 +47,5 @@ int launch_kmeans_assign(const float* x, const float* mu, int N, int D, int K, i
                          cudaStream_t st);
 int launch_kmeans_update(const float* x, const int* assign, int N, int D, int K, float* sums, int* counts,
                          cudaStream_t st);
+int launch_lse_merge(const float* part_pooled, const float* part_lse, int B, int nsplit, int P, float* pooled,
+                     float* lse, float* scratch, cudaStream_t st);

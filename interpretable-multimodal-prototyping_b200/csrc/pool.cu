@@ -662,3 +662,27 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
   }
   return IMP_OK;
 }
+
+
+// Cross-GPU merge of per-rank pooling results: rank r holds (pooled_r, lse_r) of its
+// patch shard; as a partial state that is acc = pooled_r, m = lse_r, l = 1, so the same
+// log-sum-exp merge kernel applies.  part_pooled (B, nsplit, P, 256), part_lse (B, nsplit, P).
+namespace {
+__global__ void lse_to_ml_kernel(const float* __restrict__ part_lse, float* __restrict__ ml, int P, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // over (B*nsplit, P)
+  if (i >= total) return;
+  const int bs = i / P, pi = i % P;
+  const float v = part_lse[i];
+  ml[(size_t)bs * 2 * P + pi] = v;
+  ml[(size_t)bs * 2 * P + P + pi] = (v == -INFINITY) ? 0.f : 1.f;    // an empty shard carries no mass
+}
+}  // namespace
+
+int launch_lse_merge(const float* part_pooled, const float* part_lse, int B, int nsplit, int P, float* pooled,
+                     float* lse, float* scratch, cudaStream_t st) {
+  if (B <= 0 || nsplit <= 0 || P <= 0) IMP_FAIL(IMP_ERR_ARG, "lse_merge: bad shape (%d,%d,%d)", B, nsplit, P);
+  const int total = B * nsplit * P;
+  IMP_LAUNCH("lse_to_ml", st, lse_to_ml_kernel<<<(total + 255) / 256, 256, 0, st>>>(part_lse, scratch, P, total));
+  IMP_LAUNCH("pool_merge", st, pool_merge_kernel<<<dim3(P, B), kD, 0, st>>>(part_pooled, scratch, pooled, lse, P, P, nsplit));
+  return IMP_OK;
+}

@@ -77,6 +77,9 @@ def pool_fwd(h: torch.Tensor, cu_seqlens: torch.Tensor, max_len: int, qt: torch.
     stride = 0 if qt.shape[0] == 1 and nb != 1 else p * D
     if qt.shape[0] not in (1, nb):
         raise ValueError("qt batch %d does not match %d bags" % (qt.shape[0], nb))
+    if h.shape[0] == 0 or max_len <= 0:          # an empty shard of a giant bag: no mass
+        return (torch.zeros(nb, p, D, device=h.device, dtype=torch.float32),
+                torch.full((nb, p), float("-inf"), device=h.device, dtype=torch.float32))
     pooled = torch.empty(nb, p, D, device=h.device, dtype=torch.float32)
     lse = torch.empty(nb, p, device=h.device, dtype=torch.float32)
     ws = _workspace(_lib.query("imp_pool_fwd_workspace_bytes", nb, int(max_len), p), h.device)
@@ -101,6 +104,10 @@ def pool_bwd(h: torch.Tensor, cu_seqlens: torch.Tensor, max_len: int, qt: Sequen
         qs.append(q)
         strides.append(0 if q.shape[0] == 1 and nb != 1 else q.shape[1] * D)
     p = qs[0].shape[1]
+    if h.shape[0] == 0 or max_len <= 0:
+        if want_dz and db1 is not None and not db_accumulate:
+            db1.zero_()
+        return torch.zeros(nb, p, D, device=h.device, dtype=torch.float32), (torch.empty_like(h) if want_dz else None)
     dq = torch.empty(nb, p, D, device=h.device, dtype=torch.float32)
     dz = torch.empty_like(h) if want_dz else None
     ws = _workspace(_lib.query("imp_pool_bwd_workspace_bytes", nb, int(max_len), p), h.device)
@@ -234,3 +241,14 @@ def kmeans_update(x: torch.Tensor, assign: torch.Tensor, k: int) -> Tuple[torch.
     counts = torch.zeros(k, device=x.device, dtype=torch.int32)
     _lib.call("imp_kmeans_update", x, assign, n, d, int(k), sums, counts, _lib.stream_ptr())
     return sums, counts
+
+
+def lse_merge(part_pooled: torch.Tensor, part_lse: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """part_pooled (B,S,P,256), part_lse (B,S,P): per-shard pooling results -> whole-bag (pooled, lse)."""
+    _chk(part_pooled, torch.float32, "part_pooled"); _chk(part_lse, torch.float32, "part_lse")
+    b, s, p, _ = part_pooled.shape
+    pooled = torch.empty(b, p, D, device=part_pooled.device, dtype=torch.float32)
+    lse = torch.empty(b, p, device=part_pooled.device, dtype=torch.float32)
+    scratch = torch.empty(b * s * 2 * p, device=part_pooled.device, dtype=torch.float32)
+    _lib.call("imp_lse_merge", part_pooled, part_lse, b, s, p, pooled, lse, scratch, _lib.stream_ptr())
+    return pooled, lse

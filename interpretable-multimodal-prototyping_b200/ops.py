@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import kernels
+from . import kernels, parallel
 
 D = kernels.D
 SENTINEL = -10000.0          # data/data_manager.py:387, umeml_gan.py:404
@@ -99,7 +99,7 @@ class _ProtoFusionFn(torch.autograd.Function):
     out_proj.bias, norm1.weight, norm1.bias).  Returns (c (B,P,256) fp32, h (R,256) bf16)."""
 
     @staticmethod
-    def forward(ctx, x, cu, max_len, p_drop, seed, p_proto, w1, b1, *blk):
+    def forward(ctx, x, cu, max_len, p_drop, seed, shard_group, p_proto, w1, b1, *blk):
         nblk = len(blk) // 6
         if nblk not in (1, 2):
             raise ValueError("proto_fusion supports 1 or 2 stacked blocks (reference: 2, umeml_gan.py:289)")
@@ -113,12 +113,14 @@ class _ProtoFusionFn(torch.autograd.Function):
                 in_w, in_b, out_w, out_b, ln_w, ln_b = blk[6 * k:6 * k + 6]
                 qt = fold_query(c, in_w, in_b).contiguous()
                 pooled, lse = kernels.pool_fwd(h, cu, max_len, qt)
+                if shard_group is not None:          # giant bag sharded over ranks: LSE merge of the partial states
+                    pooled, lse = parallel.merge_shards(pooled, lse, shard_group)
                 c = block_tail(c, pooled, in_w, in_b, out_w, out_b, ln_w, ln_b)
                 saved += [pooled, lse]
         if c.shape[0] != nb:
             c = c.expand(nb, -1, -1)
         ctx.save_for_backward(x, h, cu, p_proto, w1, b1, *blk, *saved)
-        ctx.nblk, ctx.max_len, ctx.p_drop = nblk, max_len, p_drop
+        ctx.nblk, ctx.max_len, ctx.p_drop, ctx.shard_group = nblk, max_len, p_drop, shard_group
         ctx.mark_non_differentiable(h)
         return c.contiguous(), h
 
@@ -164,6 +166,8 @@ class _ProtoFusionFn(torch.autograd.Function):
             else:
                 dq, dz = kernels.pool_bwd(h, cu, ctx.max_len, qts_c, dpool, lses, delta, 0, want_dz=True,
                                           relu_mask=True, keep_scale=keep_scale, db1=db1)
+            if ctx.shard_group is not None:       # every rank saw only its patches: sum the partial dq~
+                parallel.allreduce_sum_(dq, ctx.shard_group)
             if qts[k].shape[0] == 1 and dq.shape[0] != 1:
                 dq = dq.sum(0, keepdim=True)
             outs.append(qts[k])
@@ -171,13 +175,16 @@ class _ProtoFusionFn(torch.autograd.Function):
         leaves = [p_leaf] + w_leaf
         grads = torch.autograd.grad(outs, leaves, gouts, allow_unused=True)
         dw1 = kernels.pathnet_dw(dz, x)
+        if ctx.shard_group is not None:
+            parallel.allreduce_sum_(dw1, ctx.shard_group)
+            parallel.allreduce_sum_(db1, ctx.shard_group)
         need = ctx.needs_input_grad
-        res = [None, None, None, None, None,
-               grads[0] if need[5] else None,
-               dw1.to(w1.dtype) if need[6] else None,
-               db1.to(b1.dtype) if need[7] else None]
+        res = [None, None, None, None, None, None,
+               grads[0] if need[6] else None,
+               dw1.to(w1.dtype) if need[7] else None,
+               db1.to(b1.dtype) if need[8] else None]
         for i in range(6 * nblk):
-            res.append(grads[1 + i] if need[8 + i] else None)
+            res.append(grads[1 + i] if need[9 + i] else None)
         return tuple(res)
 
 
@@ -188,10 +195,13 @@ def block_params(blk: "PathProtoGenerator"):
 
 def proto_fusion(x_packed: torch.Tensor, cu_seqlens: torch.Tensor, max_len: int, p_proto: torch.Tensor,
                  w1: torch.Tensor, b1: torch.Tensor, blocks: Sequence[Sequence[torch.Tensor]],
-                 p_drop: float = 0.0, seed: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """-> (prototype tokens (B,P,256) fp32, h (R,256) bf16 for the modularity term)."""
+                 p_drop: float = 0.0, seed: int = 0, shard_group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (prototype tokens (B,P,256) fp32, h (R,256) bf16 for the modularity term).
+    ``shard_group``: a torch.distributed group whose ranks each hold a contiguous patch shard of the
+    SAME bags (giant-bag mode): partial softmax states are merged across the group."""
     flat = [t for b in blocks for t in b]
-    return _ProtoFusionFn.apply(x_packed, cu_seqlens, int(max_len), float(p_drop), int(seed), p_proto, w1, b1, *flat)
+    return _ProtoFusionFn.apply(x_packed, cu_seqlens, int(max_len), float(p_drop), int(seed), shard_group, p_proto,
+                                w1, b1, *flat)
 
 
 # ------------------------------------------------------------------------------------------

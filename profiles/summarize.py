@@ -1,0 +1,64 @@
+"""Turn ncu outputs brought back in gpurun_out/ into the compact summaries committed here.
+  python profiles/summarize.py launches gpurun_out/launches.csv  > profiles/rNN_launches.md
+  python profiles/summarize.py full gpurun_out/prof.ncu-rep      > profiles/rNN_ncu_full.md
+"""
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+    "launch__grid_size", "launch__block_size", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+]
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if r and not r[0].startswith("==")]
+    hdr = rows[0]
+    ik, iv, im = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
+    agg, order = {}, []
+    for r in rows[1:]:
+        if len(r) <= iv or r[im] != "gpu__time_duration.sum":
+            continue
+        name = r[ik].split("(")[0].replace("void ", "").replace("<unnamed>::", "")
+        t = float(r[iv].replace(",", ""))
+        if name not in agg:
+            agg[name] = [0.0, 0]
+            order.append(name)
+        agg[name][0] += t
+        agg[name][1] += 1
+    unit = rows[1][hdr.index("Metric Unit")] if len(rows) > 1 else "?"
+    tot = sum(v[0] for v in agg.values())
+    print("| kernel | launches | total (%s) | share |" % unit)
+    print("|---|---:|---:|---:|")
+    for n in sorted(agg, key=lambda k: -agg[k][0]):
+        print("| `%s` | %d | %.1f | %.1f%% |" % (n[:90], agg[n][1], agg[n][0], 100 * agg[n][0] / tot))
+    print("\ntotal over captured launches: %.1f %s (cold-cache, serialised: compare shares)" % (tot, unit))
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    for r in rows[2:]:
+        print("### `%s`\n" % r[idx["Kernel Name"]][:110])
+        print("| metric | value | unit |\n|---|---:|---|")
+        for k in KEYS:
+            if k in idx:
+                print("| %s | %s | %s |" % (k, r[idx[k]], units[idx[k]]))
+        print()
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])

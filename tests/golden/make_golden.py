@@ -98,7 +98,7 @@ def gen_model(seed):
     assert not missing.unexpected_keys, missing.unexpected_keys
     model.eval()
     torch.manual_seed(seed + 1)
-    lens, npad, G = [96, 57, 128], 128, sum(R.GROUP_SIZES)
+    lens, npad, G = [96, 57, 120], 128, sum(R.GROUP_SIZES)   # every bag shorter than npad: the reference is undefined otherwise (umeml_gan.py:405-410)
     img = torch.full((len(lens), npad, 512), -10000.0)
     for i, n in enumerate(lens):
         img[i, :n] = torch.randn(n, 512)

@@ -1,0 +1,62 @@
+"""CPU: host-side token algebra and partition planning (pure torch, no kernels)."""
+import torch
+
+from oracle import imp_oracle as O
+from util_hotpath import block_tensors, make_params, rel
+
+
+def test_fold_query_and_block_tail_equal_reference_attention():
+    from imp_b200 import ops
+    params = make_params(3)
+    in_w, in_b, out_w, out_b, ln_w, ln_b = block_tensors(params, 1)
+    g = torch.Generator().manual_seed(0)
+    h = torch.relu(torch.randn(257, 256, generator=g))
+    c = torch.randn(5, 256, generator=g)
+    qt = ops.fold_query(c, in_w, in_b)
+    assert rel(qt, O.folded_query(c, in_w, in_b)) < 1e-6
+    a = torch.softmax(qt @ h.t(), dim=1)
+    out = ops.block_tail(c, a @ h, in_w, in_b, out_w, out_b, ln_w, ln_b)
+    blk = dict(zip(["in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias", "norm1.weight", "norm1.bias"],
+                   [in_w, in_b, out_w, out_b, ln_w, ln_b]))
+    assert rel(out, O.proto_block(h, c, blk)) < 1e-5
+
+
+def test_normalize_tokens_is_across_tokens():
+    from imp_b200 import modularity as M
+    c = torch.randn(2, 7, 256)
+    ch = M.normalize_tokens(c)
+    assert torch.allclose(ch.norm(dim=1), torch.ones(2, 256), atol=1e-5)
+    x = torch.relu(torch.randn(50, 256))
+    ref = O.cluster_assignment(x, c[0])
+    xh = x / x.norm(dim=1, keepdim=True)
+    assert rel(torch.relu(xh @ ch[0].t()), ref) < 1e-6
+
+
+def test_state_dict_keys_match_reference_names():
+    from imp_b200 import model
+    net = model.IMPHotPath(n_proto=6, seed=0)
+    keys = set(net.state_dict().keys())
+    want = {"path_net.0.weight", "path_net.0.bias"}
+    for k in range(6):
+        want |= {"omic_net.%d.0.weight" % k, "omic_net.%d.0.bias" % k}
+    for b in range(2):
+        p = "proto_g_blocks.%d." % b
+        want |= {p + "cross_attn.in_proj_weight", p + "cross_attn.in_proj_bias", p + "cross_attn.out_proj.weight",
+                 p + "cross_attn.out_proj.bias", p + "norm1.weight", p + "norm1.bias"}
+    assert keys == want, keys ^ want
+    assert net.state_dict()["omic_net.4.0.weight"].shape == (256, 1538)
+    assert net.p_proto.shape == (1, 6, 256) and "p_proto" not in keys         # plain tensor, like the reference
+    assert net.p_proto.abs().max().item() <= 1 / 6 + 1e-6
+
+
+def test_shard_bounds_and_slide_assignment():
+    from imp_b200 import parallel as P
+    for n, w in [(120000, 8), (100, 8), (64, 2), (1, 4), (16384, 3)]:
+        b = P.shard_bounds(n, w)
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        assert all(s % P.TILE == 0 for s, _ in b if s < n)
+    lens = [9000, 100, 5000, 4900, 50, 8000, 3000]
+    a = P.assign_slides(lens, 3)
+    assert sorted(i for r in a for i in r) == list(range(len(lens)))
+    loads = [sum(lens[i] for i in r) for r in a]
+    assert max(loads) - min(loads) <= max(lens)
