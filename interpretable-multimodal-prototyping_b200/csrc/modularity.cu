@@ -245,7 +245,7 @@ modularity_gram_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       k1 = (float)(1.0 / e);
       k2 = (float)(1.0 / (e * e));
     }
-    const float x2scale = 2.f * 1.4426950408889634f * p.inv_temp;     // tanh(u/temp) via exp2(-2 u log2e / temp)
+    const float nx2scale = -2.f * 1.4426950408889634f * p.inv_temp;   // tanh(u/temp) via exp2(-2 u log2e / temp)
     const float gscale = -200.f * p.inv_temp;                        // 2 * (-100) / temp
     for (int it = 0; it < ntiles; ++it) {
       const int stage = it % kStages, acc = it & 1;
@@ -270,44 +270,68 @@ modularity_gram_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
         const uint8_t* st = s_stage + (size_t)stage * kStageBytes + kBBytes;
         const int4* sL = reinterpret_cast<const int4*>(st) + (size_t)hc * 32 * (PtPad / 4);
         const float dj_lane = (jbase + lane < row_end) ? __ldg(p.d + jbase + lane) : 0.f;
+        // Two columns per step and four independent add-max chains per token group (a dependent
+        // VIADDMNMX issues only every ~5 cycles), software-pipelined: the chains of columns jj+2,jj+3
+        // are issued before the exp2/rcp tail of columns jj,jj+1 so the MUFU latency hides behind them.
+        auto chains = [&](int jj, int (&mg0)[2], int (&mg1)[2]) {
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const int j = jbase + jj;
-          const bool ok = row_ok && j < row_end;
-          const float a = (ok && j != i) ? fmaxf(__uint_as_float(v[jj]), 0.f) : 0.f;
-          const float djv = __shfl_sync(0xffffffffu, dj_lane, jj);     // warp-uniform: never under a lane predicate
-          const float dd = ok ? di * djv : 0.f;
-          const int4* lj = sL + jj * (PtPad / 4);
-          int m0 = INT_MIN, m1 = INT_MIN;
+          for (int c = 0; c < 2; ++c) {
+            const int4* lj = sL + (jj + c) * (PtPad / 4);
+            int ch[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
 #pragma unroll
-          for (int qd = 0; qd < NQ1; ++qd) {
-            const int4 w = lj[qd];
-            m0 = __viaddmax_s32(Li[4 * qd + 0], w.x, m0);
-            m0 = __viaddmax_s32(Li[4 * qd + 1], w.y, m0);
-            m0 = __viaddmax_s32(Li[4 * qd + 2], w.z, m0);
-            m0 = __viaddmax_s32(Li[4 * qd + 3], w.w, m0);
+            for (int qd = 0; qd < NQ1; ++qd) {
+              const int4 w = lj[qd];
+              ch[0] = __viaddmax_s32(Li[4 * qd + 0], w.x, ch[0]);
+              ch[1] = __viaddmax_s32(Li[4 * qd + 1], w.y, ch[1]);
+              ch[2] = __viaddmax_s32(Li[4 * qd + 2], w.z, ch[2]);
+              ch[3] = __viaddmax_s32(Li[4 * qd + 3], w.w, ch[3]);
+            }
+            mg0[c] = max(__vimax3_s32(ch[0], ch[1], ch[2]), ch[3]);
+            int cg[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
+#pragma unroll
+            for (int qd = 0; qd < NQ2; ++qd) {
+              const int4 w = lj[NQ1 + qd];
+              cg[0] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 0], w.x, cg[0]);
+              cg[1] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 1], w.y, cg[1]);
+              cg[2] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 2], w.z, cg[2]);
+              cg[3] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 3], w.w, cg[3]);
+            }
+            mg1[c] = max(__vimax3_s32(cg[0], cg[1], cg[2]), cg[3]);
           }
+        };
+        auto tail = [&](int jj, const int (&mg0)[2], const int (&mg1)[2]) {
 #pragma unroll
-          for (int qd = 0; qd < NQ2; ++qd) {
-            const int4 w = lj[NQ1 + qd];
-            m1 = __viaddmax_s32(Li[4 * (NQ1 + qd) + 0], w.x, m1);
-            m1 = __viaddmax_s32(Li[4 * (NQ1 + qd) + 1], w.y, m1);
-            m1 = __viaddmax_s32(Li[4 * (NQ1 + qd) + 2], w.z, m1);
-            m1 = __viaddmax_s32(Li[4 * (NQ1 + qd) + 3], w.w, m1);
-          }
-          const float gw = gscale * (a * k1 - dd * k2);
+          for (int c = 0; c < 2; ++c) {
+            const int j = jbase + jj + c;
+            const bool ok = row_ok && j < row_end;
+            const float a = (ok && j != i) ? fmaxf(__uint_as_float(v[jj + c]), 0.f) : 0.f;
+            const float djv = __shfl_sync(0xffffffffu, dj_lane, jj + c);   // warp-uniform: never under a lane predicate
+            const float dd = ok ? di * djv : 0.f;
+            const float gw4 = 4.f * gscale * (a * k1 - dd * k2);           // 0 for masked pairs
 #pragma unroll
-          for (int grp = 0; grp < (NQ2 ? 2 : 1); ++grp) {
-            const int m = grp ? m1 : m0;
-            const int pstar = (m & 31) + (grp ? 4 * NQ1 : 0);
-            const float u = ex2_approx((float)(m >> 5) * (1.f / (float)(1 << kLogShift)));
-            const float e2 = ex2_approx(-u * x2scale);
-            const float r = rcp_approx(1.f + e2);
-            const float delta = (1.f - e2) * r;
-            s1[grp] += a * delta;
-            s2[grp] += dd * delta;
-            myT[pstar] += gw * (4.f * e2 * r * r) * u;
+            for (int grp = 0; grp < (NQ2 ? 2 : 1); ++grp) {
+              const int m = grp ? mg1[c] : mg0[c];
+              const int pstar = (m & 31) + (grp ? 4 * NQ1 : 0);
+              // the 5 index bits perturb log2(u) by < 2^-16: far below the fixed-point resolution that matters
+              const float u = ex2_approx((float)m * (1.f / (float)(1 << (kLogShift + 5))));
+              const float e2 = ex2_approx(u * nx2scale);             // exp(-2u/temp)
+              const float r = rcp_approx(1.f + e2);
+              const float t1 = e2 * r;
+              const float delta = r - t1;                            // tanh(u/temp) = (1-e2)/(1+e2)
+              s1[grp] = fmaf(a, delta, s1[grp]);
+              s2[grp] = fmaf(dd, delta, s2[grp]);
+              myT[pstar] += (gw4 * t1) * (r * u);                    // 2 g (1-delta^2)/temp * u,  1-delta^2 = 4 e2 r^2
+            }
           }
+        };
+        int ma0[2], ma1[2];
+        chains(0, ma0, ma1);
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 2) {
+          int mb0[2] = {INT_MIN, INT_MIN}, mb1[2] = {INT_MIN, INT_MIN};
+          if (jj + 2 < 32) chains(jj + 2, mb0, mb1);
+          tail(jj, ma0, ma1);
+          ma0[0] = mb0[0]; ma0[1] = mb0[1]; ma1[0] = mb1[0]; ma1[1] = mb1[1];
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
