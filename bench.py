@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--bags", type=int, default=16, help="slides per step per GPU")
+    ap.add_argument("--bags", type=int, default=32, help="slides per step per GPU")
     ap.add_argument("--e2e-bags", type=int, default=4, help="slides per step of the host-buffer (e2e) leg")
     ap.add_argument("--patches", type=int, default=N_PATCH)
     ap.add_argument("--protos", type=int, default=N_PROTO)
@@ -257,6 +257,7 @@ def run_ours(args):
         "pool_fwd": ("hbm", rows * 256 * 2.0), "pool_bwd_dq": ("hbm", rows * 256 * 2.0),
         "pool_bwd_dz": ("hbm", rows * 256 * 2.0 * 2),
         "modularity_gram_degrees": ("tensor", 2.0 * B * N * N * 256), "modularity_gram_main": ("tensor", 2.0 * B * N * N * 256),
+        "modularity_pairs": ("tensor", 1.0 * B * N * N * 256),
     }
     kernels_out = []
     tot_kernel_ms = sum(v["ms_per_step"] for v in pk.values()) or 1.0

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "launchers.h"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace {
 
@@ -192,7 +193,7 @@ modularity_gram_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_a + bx * (kBM * 128), &tm_a, afull, bx * 64, i0);
       for (int it = 0; it < ntiles; ++it) {
         const int stage = it % kStages;
-        mbar_wait(&empty[stage], ((it / kStages) & 1) ^ 1);
+        mbar_wait_idle(&empty[stage], ((it / kStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&full[stage], kBBytes + kLBytes);
         uint8_t* dst = s_stage + (size_t)stage * kStageBytes;
         const int j0 = row_begin + (t0 + it) * kBN;
@@ -205,13 +206,13 @@ modularity_gram_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
-      mbar_wait(afull, 0);
+      mbar_wait_idle(afull, 0);
       tc_fence_after();
       const uint32_t sa = smem_u32(s_a);
       for (int it = 0; it < ntiles; ++it) {
         const int stage = it % kStages, acc = it & 1;
-        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
-        mbar_wait(&full[stage], (it / kStages) & 1);
+        mbar_wait_idle(&tempty[acc], ((it >> 1) & 1) ^ 1);
+        mbar_wait_idle(&full[stage], (it / kStages) & 1);
         tc_fence_after();
         const uint32_t sb = smem_u32(s_stage + (size_t)stage * kStageBytes);
 #pragma unroll
@@ -259,11 +260,24 @@ modularity_gram_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       if (lane == 0) mbar_arrive(&tempty[acc]);      // accumulator is in registers: release TMEM early
       const int jbase = row_begin + (t0 + it) * kBN + hc * 32;
       if (MODE == 0) {
+        // interior tiles (no diagonal, no bag end) need no per-pair masks: relu + add only
+        const int jt0 = row_begin + (t0 + it) * kBN;
+        const bool interior = (jt0 + kBN <= row_end) && (jt0 >= i0 + kBM || jt0 + kBN <= i0);
+        if (interior) {
+          float p0 = 0.f, p1 = 0.f;
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const int j = jbase + jj;
-          const float a = fmaxf(__uint_as_float(v[jj]), 0.f);
-          acc_d += (j < row_end && j != i) ? a : 0.f;
+          for (int jj = 0; jj < 32; jj += 2) {
+            p0 += fmaxf(__uint_as_float(v[jj]), 0.f);
+            p1 += fmaxf(__uint_as_float(v[jj + 1]), 0.f);
+          }
+          acc_d += p0 + p1;
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = jbase + jj;
+            const float a = fmaxf(__uint_as_float(v[jj]), 0.f);
+            acc_d += (j < row_end && j != i) ? a : 0.f;
+          }
         }
       } else {
         mbar_wait(&full[stage], (it / kStages) & 1);           // L tile of this stage
@@ -378,6 +392,278 @@ modularity_gram_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------
+// Symmetric pair sweep (traces + T).  Every unordered patch pair {i,j}, i <= j, is evaluated once by
+// the CTA that owns row i: CTA = 128 rows x the 32-column tiles at or right of its diagonal.
+//   thread = (row i, 16 of the 32 columns).  Row side: T_i[p*] += t in a private smem row.
+//   Column side: (t | p*) words go through a warp-private smem transpose so that lane = column owns
+//   the update T_j[p*] += t (no atomics in the loop); column accumulators are flushed to global
+//   memory per tile with one RED per non-zero entry.
+// ------------------------------------------------------------------------------------------
+constexpr int kPN = 32;                               // columns per tile of the pair sweep
+constexpr int kPBBytes = kPN * kD * 2;                // 16 KB, four [32][64] boxes
+constexpr int kXWords = 2 * 16 * 33;                  // per warp: [group][column][row + pad]
+
+template <int NQ1, int NQ2>
+constexpr size_t pairs_smem() {
+  constexpr int PtPad = 4 * (NQ1 + NQ2);
+  size_t stage = (kPBBytes + (size_t)kPN * PtPad * 4 + 1023) & ~(size_t)1023;
+  size_t t = 2 * (size_t)kEpiWarps * 32 * (PtPad + 1) * 4;
+  return 1024 + kABytes + kStages * stage + t + (size_t)kEpiWarps * kXWords * 4 + 256;
+}
+
+template <int NQ1, int NQ2>
+__global__ void __launch_bounds__(kThreads, 1)
+modularity_pairs_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                        const GramParams p) {
+  constexpr int PtPad = 4 * (NQ1 + NQ2);
+  constexpr int kLBytes = kPN * PtPad * 4;
+  constexpr int kStageBytes = (kPBBytes + kLBytes + 1023) & ~1023;
+  constexpr int TS = PtPad + 1;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* s_a = smem;
+  uint8_t* s_stage = s_a + kABytes;
+  float* s_Trow = reinterpret_cast<float*>(s_stage + kStages * kStageBytes);
+  float* s_Tcol = s_Trow + kEpiWarps * 32 * TS;
+  uint32_t* s_X = reinterpret_cast<uint32_t*>(s_Tcol + kEpiWarps * 32 * TS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_X + kEpiWarps * kXWords);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* afull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
+  float* s_red = reinterpret_cast<float*>(tmem_slot + 2);
+
+  const int b = blockIdx.x, rb = blockIdx.z;          // bags vary fastest: the heavy row blocks (rb = 0) start first
+  const int row_begin = __ldg(p.cu + b), row_end = __ldg(p.cu + b + 1);
+  const int n = row_end - row_begin;
+  const int i0 = row_begin + rb * kBM;
+  if (i0 >= row_end) return;
+  const int ntiles_bag = (n + kPN - 1) / kPN;
+  const int t_lo = rb * (kBM / kPN);                       // first tile that touches the diagonal block
+  const int per = (ntiles_bag - t_lo + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int t0 = t_lo + blockIdx.y * per;
+  const int ntiles = max(0, min(ntiles_bag, t0 + per) - t0);
+  if (ntiles == 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == kEpiWarps && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
+    mbar_init(afull, 1);
+    mbar_fence_init();
+  }
+  if (warp == kEpiWarps + 1) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kEpiWarps) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(afull, kABytes);
+#pragma unroll
+      for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_a + bx * (kBM * 128), &tm_a, afull, bx * 64, i0);
+      for (int it = 0; it < ntiles; ++it) {
+        const int stage = it % kStages;
+        mbar_wait_idle(&empty[stage], ((it / kStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[stage], kPBBytes + kLBytes);
+        uint8_t* dst = s_stage + (size_t)stage * kStageBytes;
+        const int j0 = row_begin + (t0 + it) * kPN;
+#pragma unroll
+        for (int bx = 0; bx < 4; ++bx) tma_load_2d(dst + bx * (kPN * 128), &tm_b, &full[stage], bx * 64, j0);
+        bulk_load(dst + kPBBytes, p.lfix + (size_t)j0 * PtPad, kLBytes, &full[stage]);
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, kPN, 0, 0);
+      mbar_wait_idle(afull, 0);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(s_a);
+      for (int it = 0; it < ntiles; ++it) {
+        const int stage = it % kStages, acc = it & 1;
+        mbar_wait_idle(&tempty[acc], ((it >> 1) & 1) ^ 1);
+        mbar_wait_idle(&full[stage], (it / kStages) & 1);
+        tc_fence_after();
+        const uint32_t sb = smem_u32(s_stage + (size_t)stage * kStageBytes);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) {
+          const uint64_t ad = umma_desc_sw128(sa + (k >> 2) * (kBM * 128) + (k & 3) * 32, 0, 1024);
+          const uint64_t bd = umma_desc_sw128(sb + (k >> 2) * (kPN * 128) + (k & 3) * 32, 0, 1024);
+          umma_f16(tmem_base + acc * kPN, ad, bd, idesc, k != 0);
+        }
+        umma_commit(&empty[stage]);
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3, hc = warp >> 2;
+    const int i = i0 + q * 32 + lane;
+    const bool row_ok = i < row_end;
+    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+    int Li[PtPad];
+    float* myTrow = s_Trow + (size_t)(warp * 32 + lane) * TS;
+    float* myTcol = s_Tcol + (size_t)(warp * 32 + lane) * TS;
+    uint32_t* myX = s_X + (size_t)warp * kXWords;
+#pragma unroll
+    for (int k = 0; k < PtPad; ++k) {
+      Li[k] = row_ok ? (__ldg(p.lfix + (size_t)i * PtPad + k) & ~31) : (kZeroFix * 32);
+      myTrow[k] = 0.f;
+      myTcol[k] = 0.f;
+    }
+    const float di = row_ok ? __ldg(p.d + i) : 0.f;
+    const double e = p.e[b];
+    const float k1 = (float)(1.0 / e), k2 = (float)(1.0 / (e * e));
+    const float nx2scale = -2.f * 1.4426950408889634f * p.inv_temp;
+    const float gscale4 = -800.f * p.inv_temp;                          // 4 * 2 * (-100) / temp
+    const int cx = lane & 15, hx = lane >> 4;                           // column-phase role of this lane
+    for (int it = 0; it < ntiles; ++it) {
+      const int stage = it % kStages, acc = it & 1;
+      mbar_wait(&tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kPN + hc * 16, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      const int jbase = row_begin + (t0 + it) * kPN + hc * 16;
+      mbar_wait(&full[stage], (it / kStages) & 1);
+      const uint8_t* st = s_stage + (size_t)stage * kStageBytes + kPBBytes;
+      const int4* sL = reinterpret_cast<const int4*>(st) + (size_t)hc * 16 * (PtPad / 4);
+      const float dj_lane = (jbase + cx < row_end) ? __ldg(p.d + jbase + cx) : 0.f;
+
+      auto chains = [&](int jj, int (&mg0)[2], int (&mg1)[2]) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int4* lj = sL + (jj + c) * (PtPad / 4);
+          int ch[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
+#pragma unroll
+          for (int qd = 0; qd < NQ1; ++qd) {
+            const int4 w = lj[qd];
+            ch[0] = __viaddmax_s32(Li[4 * qd + 0], w.x, ch[0]);
+            ch[1] = __viaddmax_s32(Li[4 * qd + 1], w.y, ch[1]);
+            ch[2] = __viaddmax_s32(Li[4 * qd + 2], w.z, ch[2]);
+            ch[3] = __viaddmax_s32(Li[4 * qd + 3], w.w, ch[3]);
+          }
+          mg0[c] = max(__vimax3_s32(ch[0], ch[1], ch[2]), ch[3]);
+          int cg[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
+#pragma unroll
+          for (int qd = 0; qd < NQ2; ++qd) {
+            const int4 w = lj[NQ1 + qd];
+            cg[0] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 0], w.x, cg[0]);
+            cg[1] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 1], w.y, cg[1]);
+            cg[2] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 2], w.z, cg[2]);
+            cg[3] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 3], w.w, cg[3]);
+          }
+          mg1[c] = max(__vimax3_s32(cg[0], cg[1], cg[2]), cg[3]);
+        }
+      };
+      auto tail = [&](int jj, const int (&mg0)[2], const int (&mg1)[2]) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int j = jbase + jj + c;
+          const bool ok = row_ok && j < row_end && j >= i;                 // upper triangle + diagonal only
+          const float sym = j > i ? 2.f : 1.f;                             // an unordered pair stands for (i,j) and (j,i)
+          const float a = (ok && j != i) ? fmaxf(__uint_as_float(v[jj + c]), 0.f) : 0.f;
+          const float djv = __shfl_sync(0xffffffffu, dj_lane, jj + c);     // warp-uniform: never under a lane predicate
+          const float dd = ok ? di * djv : 0.f;
+          const float gw4 = gscale4 * (a * k1 - dd * k2);                  // 0 for masked pairs
+          const float as = a * sym, ds = dd * sym;
+#pragma unroll
+          for (int grp = 0; grp < (NQ2 ? 2 : 1); ++grp) {
+            const int m = grp ? mg1[c] : mg0[c];
+            const int pl = m & 31;
+            const float u = ex2_approx((float)m * (1.f / (float)(1 << (kLogShift + 5))));
+            const float e2 = ex2_approx(u * nx2scale);
+            const float r = rcp_approx(1.f + e2);
+            const float t1 = e2 * r;
+            const float delta = r - t1;
+            s1[grp] = fmaf(as, delta, s1[grp]);
+            s2[grp] = fmaf(ds, delta, s2[grp]);
+            const float t = (gw4 * t1) * (r * u);
+            myTrow[pl + (grp ? 4 * NQ1 : 0)] += t;
+            // column side: (t | p*) to the transpose buffer; the diagonal pair has no mirror image
+            const uint32_t word = j > i ? ((__float_as_uint(t) & ~31u) | (uint32_t)pl) : (uint32_t)pl;
+            myX[(grp * 16 + jj + c) * 33 + lane] = word;
+          }
+        }
+      };
+      int ma0[2], ma1[2];
+      chains(0, ma0, ma1);
+#pragma unroll
+      for (int jj = 0; jj < 16; jj += 2) {
+        int mb0[2] = {INT_MIN, INT_MIN}, mb1[2] = {INT_MIN, INT_MIN};
+        if (jj + 2 < 16) chains(jj + 2, mb0, mb1);
+        tail(jj, ma0, ma1);
+        ma0[0] = mb0[0]; ma0[1] = mb0[1]; ma1[0] = mb1[0]; ma1[1] = mb1[1];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      // ---- column phase: lane (cx, hx) folds rows hx*16..+15 of column cx into its private accumulators ----
+#pragma unroll
+      for (int grp = 0; grp < (NQ2 ? 2 : 1); ++grp) {
+        const uint32_t* col = myX + (grp * 16 + cx) * 33 + hx * 16;
+#pragma unroll 4
+        for (int r = 0; r < 16; ++r) {
+          const uint32_t w = col[r];
+          myTcol[(w & 31u) + (grp ? 4 * NQ1 : 0)] += __uint_as_float(w & ~31u);
+        }
+      }
+      // ---- combine the 8 partial accumulators of every column inside the CTA, one RED per non-zero ----
+      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+      {
+        const int jt0 = row_begin + (t0 + it) * kPN;
+        for (int ent = threadIdx.x; ent < kPN * PtPad; ent += kEpiWarps * 32) {
+          const int c32 = ent / PtPad, k = ent - c32 * PtPad;
+          float* base = s_Tcol + (size_t)(((c32 >> 4) * 4) * 32 + (c32 & 15)) * TS + k;   // warp (hc*4+q), lane hx*16+cx
+          float tsum = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              float* ptr = base + (size_t)(qq * 32 + hh * 16) * TS;
+              tsum += *ptr;
+              *ptr = 0.f;
+            }
+          if (tsum != 0.f && jt0 + c32 < row_end) atomicAdd(p.T + (size_t)(jt0 + c32) * PtPad + k, tsum);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+      __syncwarp();                                   // X is rewritten by the next tile
+    }
+    if (row_ok) {
+#pragma unroll 4
+      for (int k = 0; k < PtPad; ++k) {
+        const float t = myTrow[k];
+        if (t != 0.f) atomicAdd(p.T + (size_t)i * PtPad + k, t);
+      }
+    }
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp) {
+      const float a1 = warp_sum(s1[grp]), a2 = warp_sum(s2[grp]);
+      if (lane == 0) { s_red[warp * 4 + grp * 2] = a1; s_red[warp * 4 + grp * 2 + 1] = a2; }
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+    if (threadIdx.x < 4) {
+      double t = 0.0;
+      for (int w = 0; w < kEpiWarps; ++w) t += (double)s_red[w * 4 + threadIdx.x];
+      atomicAdd(p.s + (size_t)b * 4 + threadIdx.x, t);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // finish: dC = T / C (C = exp2(L)), dchat_p = sum_i dC_ip xh_i ; loss per group
 //   grid (row chunks, B), 256 threads = features; dchat accumulated with atomicAdd
 // ------------------------------------------------------------------------------------------
@@ -460,6 +746,19 @@ int run_gram(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p, 
   return IMP_OK;
 }
 
+template <int NQ1, int NQ2>
+int run_pairs(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = pairs_smem<NQ1, NQ2>();
+  static_assert(smem <= 227 * 1024, "modularity_pairs shared memory");
+  static bool done = false;
+  if (!done) {
+    IMP_CUDA(cudaFuncSetAttribute(modularity_pairs_kernel<NQ1, NQ2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done = true;
+  }
+  IMP_LAUNCH("modularity_pairs", st, modularity_pairs_kernel<NQ1, NQ2><<<grid, kThreads, smem, st>>>(ta, tb, p));
+  return IMP_OK;
+}
+
 struct Carve {
   bf16* xh; float* invn; int* lfix; float* d; float* T; double* e; double* s;
   size_t zero_off, zero_bytes, total;
@@ -533,7 +832,13 @@ int launch_modularity(const bf16* h, int total_rows, const int* cu, int B, int m
   nsplit = (col_tiles + gp.tiles_per_split - 1) / gp.tiles_per_split;
   const dim3 grid(row_blocks, nsplit, B);
   if ((rc = run_gram<0, 2, 0>(ta, tb, gp, grid, st))) return rc;
-#define IMP_GRAM(a, b2) rc = run_gram<1, a, b2>(ta, tb, gp, grid, st)
+  CUtensorMap tp;
+  if ((rc = imp_make_tmap_2d(&tp, c.xh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, rpad, kD * 2, 64, kPN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  // pair sweep: triangular work per row block; split the column range so that >= 2 waves of CTAs exist
+  int psplit = std::max(1, std::min((2 * imp_num_sms() + row_blocks * B - 1) / (row_blocks * B), std::max(1, col_tiles / 8)));
+  const dim3 pgrid(B, psplit, row_blocks);
+  static const bool symmetric = []() { const char* e = getenv("IMP_MODULARITY_SYMMETRIC"); return e ? atoi(e) != 0 : false; }();   // measured on B200: the full sweep is (slightly) faster, see DESIGN.md 5
+#define IMP_GRAM(a, b2) rc = symmetric ? run_pairs<a, b2>(ta, tp, gp, pgrid, st) : run_gram<1, a, b2>(ta, tb, gp, grid, st)
   if (nq2 == 0) { if (nq1 == 2) IMP_GRAM(2, 0); else if (nq1 == 4) IMP_GRAM(4, 0); else IMP_GRAM(8, 0); }
   else if (nq2 == 2) { if (nq1 == 2) IMP_GRAM(2, 2); else if (nq1 == 4) IMP_GRAM(4, 2); else IMP_GRAM(8, 2); }
   else IMP_FAIL(IMP_ERR_ARG, "modularity: second token group supports at most 8 tokens (got %d)", P2);

@@ -52,3 +52,29 @@ def test_modularity_batched_varlen_matches_single():
     for i, n in enumerate(lens):
         single = M.compute_modularity(cs[i].cuda().unsqueeze(0), hs[i].cuda().float().unsqueeze(0))
         assert abs(batched[i, 0].item() - single.item()) <= 1e-4 * abs(single.item()) + 1e-6
+
+
+def test_symmetric_pair_sweep_matches_full_sweep():
+    """The upper-triangular sweep (IMP_MODULARITY_SYMMETRIC=1) and the default full sweep are two kernels
+    for the same sums: run both in fresh processes (the switch is read once) and compare."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests');"
+        "import imp_b200; from imp_b200 import modularity as M; from test_modularity_gpu import _inputs;"
+        "h, c1, c2 = _inputs(1500, 32, 7, 3); cu = torch.tensor([0, 1500], dtype=torch.int32, device='cuda');"
+        "a = c1.cuda().unsqueeze(0).requires_grad_(True); b = c2.cuda().unsqueeze(0).requires_grad_(True);"
+        "l = M.modularity_terms(h.cuda(), cu, 1500, a, b); (l[0,0] + l[0,1]).backward();"
+        "print('RES', l[0,0].item(), l[0,1].item(), a.grad.norm().item(), b.grad.norm().item(), a.grad[0,3,5].item())"
+    ) % (root, root)
+    outs = []
+    for sym in ("0", "1"):
+        env = dict(os.environ, IMP_MODULARITY_SYMMETRIC=sym)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("RES")][-1]
+        outs.append([float(x) for x in line.split()[1:]])
+    for x, y in zip(*outs):
+        assert abs(x - y) <= 2e-4 * abs(y) + 1e-6, outs

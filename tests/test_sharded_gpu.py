@@ -1,0 +1,91 @@
+"""2 GPUs, NCCL: (a) a bag sharded over ranks (LSE merge of the partial softmax states, all-reduced
+dq~/dW1) reproduces the single-GPU tokens and gradients; (b) slide-parallel gradient all-reduce equals
+the single-GPU gradients over all slides.  Skipped with fewer than 2 GPUs."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import imp_b200  # noqa: F401
+        from imp_b200 import ops, parallel as P, step as S
+        from util_hotpath import block_tensors, make_bags, make_params, rel
+        dev = torch.device("cuda", rank)
+        params = make_params(0)
+        g = torch.Generator().manual_seed(5)
+        npatch, nproto = 5000, 16
+        bag = make_bags([npatch], 1)[0].bfloat16()
+        p_proto = ((torch.rand(1, nproto, 256, generator=g) * 2 - 1) / nproto).to(dev)
+        cot = torch.randn(1, nproto, 256, generator=g).to(dev)
+
+        def run(x, shard_group):
+            leaves = {k: v.clone().to(dev).requires_grad_(True) for k, v in params.items()}
+            cu = torch.tensor([0, x.shape[0]], dtype=torch.int32, device=dev)
+            blocks = [block_tensors(leaves, 0), block_tensors(leaves, 1)]
+            c, _ = ops.proto_fusion(x.to(dev).contiguous(), cu, max(1, x.shape[0]), p_proto, leaves["path_net.0.weight"],
+                                    leaves["path_net.0.bias"], blocks, shard_group=shard_group)
+            (c * cot).sum().backward()
+            return c.detach(), {k: v.grad for k, v in leaves.items()}
+
+        a, b = P.shard_bounds(npatch, world)[rank]
+        c_sh, g_sh = run(bag[a:b], dist.group.WORLD)
+        c_full, g_full = run(bag, None)
+        err_c = rel(c_sh, c_full)
+        err_g = max(rel(g_sh[k], g_full[k]) for k in g_full)
+
+        # slide parallel
+        lens = [700, 300, 512, 900]
+        bags = [t.bfloat16() for t in make_bags(lens, 2)]
+        cot2 = torch.randn(len(lens), nproto, 256, generator=g).to(dev)
+
+        def run_slides(idx):
+            leaves = torch.nn.ParameterDict({k.replace(".", "_"): torch.nn.Parameter(v.clone().to(dev)) for k, v in params.items()})
+            L = {k: leaves[k.replace(".", "_")] for k in params}
+            x = torch.cat([bags[i] for i in idx]).to(dev).contiguous()
+            cu = ops._cu_from_lengths([lens[i] for i in idx], dev)
+            c, _ = ops.proto_fusion(x, cu, max(lens), p_proto, L["path_net.0.weight"], L["path_net.0.bias"],
+                                    [block_tensors(L, 0), block_tensors(L, 1)])
+            (c * cot2[idx]).sum().backward()
+            return leaves
+
+        mine = P.assign_slides(lens, world)[rank]
+        lv = run_slides(mine)
+        S.allreduce_gradients(lv, world)
+        full = run_slides(list(range(len(lens))))
+        err_dp = max(rel(lv[k].grad * world, full[k].grad) for k in full.keys())
+        q.put((rank, err_c, err_g, err_dp))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_bag_and_slide_parallel():
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err_c, err_g, err_dp in res:
+        assert err_c < 2e-4, (rank, err_c)          # same kernels, different split of the softmax
+        assert err_g < 2e-3, (rank, err_g)
+        assert err_dp < 2e-3, (rank, err_dp)
