@@ -23,6 +23,8 @@
 #include "launchers.h"
 #include <algorithm>
 #include <stdlib.h>
+#include <type_traits>
+#include <limits.h>
 
 namespace {
 
@@ -34,8 +36,16 @@ constexpr int kBBytes = kBN * kD * 2;    // 32 KB, four [64][64] boxes
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kStages = 2;
-constexpr int kLogShift = 16;            // fixed point: log2(C) * 2^16, then << 5 with the token index below
-constexpr int kZeroFix = -30000000;      // "C == 0" marker (two of them still fit in int32 after << 5)
+// Fixed-point log-assignments: N = round((kCOff - log2 C) * 2^kLogShift) in [0, kNMax]  (C <= 2^kCOff = 16 by
+// Cauchy-Schwarz: |xh| = 1, |chat_p| <= sqrt(256)); C == 0 (or below 2^-28) is kNMax.  Both operands are stored
+// as integer-valued FLOATS: the column operand is (N << 5) | token index, the row operand 2^23 + (N << 5).  Their
+// fp32 sum is exact (an integer below 2^24) and its bit pattern is kMagic + ((N_i + N_j) << 5 | p): the minimum
+// over tokens yields the winning log-product and the arg-min in one word, with no int<->float conversion.
+constexpr int kLogShift = 12;
+constexpr int kNMax = (1 << 17) - 1;
+constexpr int kCOff = 4;
+constexpr int kMagic = 0x4B000000;
+constexpr float kArgOff = 64.f + 2.f * kCOff;   // undoes 2^23 * 2^-(kLogShift+5) and the two offsets
 
 // pointer arithmetic (not an integer round trip) so the compiler keeps the shared address space
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
@@ -66,7 +76,7 @@ struct PrepParams {
   const float* chat;        // (B, Pt, 256): tokens normalised across tokens per feature
   bf16* xh;                 // (Rpad,256)
   float* invn;              // (Rpad)
-  int* lfix;                // (Rpad, PtPad)
+  float* lfix;              // (Rpad, PtPad) integer-valued floats
   int B, P1, P2, P1pad, PtPad;
 };
 
@@ -107,58 +117,50 @@ __global__ void __launch_bounds__(256) modularity_prep_kernel(const PrepParams p
       dot = warp_sum(dot);
       if (lane == 0) {
         const bool real = slot < p.P1 || (slot >= p.P1pad && slot - p.P1pad < p.P2);
-        int fix = kZeroFix;
-        if (real && dot > 0.f) fix = max(kZeroFix, __float2int_rn(log2f(dot) * (float)(1 << kLogShift)));
+        int fix = kNMax;
+        if (real && dot > 0.f) fix = min(kNMax, max(0, __float2int_rn(((float)kCOff - log2f(dot)) * (float)(1 << kLogShift))));
         // low 5 bits: token index inside its group (column-side operand); the row side masks them off
-        p.lfix[(size_t)row * p.PtPad + slot] = fix * 32 + (slot < p.P1pad ? slot : slot - p.P1pad);
+        p.lfix[(size_t)row * p.PtPad + slot] = (float)(fix * 32 + (slot < p.P1pad ? slot : slot - p.P1pad));
       }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// Gram sweep.  MODE 0: degrees.  MODE 1: traces + T.   NQ1/NQ2: int4 quads per token group.
+// Degrees of a general (signed) patch graph:  d_i = sum_{j != i} relu(xh_i . xh_j),  e = sum_i d_i.
+//   CTA = 128 rows x a range of 64-column tiles; A block resident in smem, B tiles by TMA (2 stages),
+//   tcgen05 128x64x256 into two TMEM buffers; 8 epilogue warps, thread = (row, 32 of the 64 columns).
 // ------------------------------------------------------------------------------------------
 struct GramParams {
   const int* cu;
-  const int* lfix;          // (Rpad, PtPad)
-  float* d;                 // (Rpad) degrees: written (atomicAdd) in MODE 0, read in MODE 1
+  const float* lfix;        // (Rpad, PtPad)
+  float* d;                 // (Rpad) degrees
   double* e;                // (B)
   float* T;                 // (Rpad, PtPad) atomicAdd
-  double* s;                // (B, 2 groups, 2): s1, s2
+  double* s;                // (B, 2 groups): sum_ij (A_ij/e - d_i d_j/e^2) delta_ij
+  const int* nonneg;        // (1) device flag: 1 when every element of h is >= 0 (closed-form degrees were used)
   int tiles_per_split;      // column tiles per CTA
   float inv_temp;
 };
 
-template <int MODE, int NQ1, int NQ2>
-constexpr size_t gram_smem() {
-  constexpr int PtPad = 4 * (NQ1 + NQ2);
-  size_t stage = kBBytes + (MODE ? (size_t)kBN * PtPad * 4 : 0);
-  size_t t = MODE ? (size_t)kEpiWarps * 32 * (PtPad + 1) * 4 : 0;
-  return 1024 + kABytes + kStages * ((stage + 1023) & ~(size_t)1023) + t + 256;
-}
+constexpr size_t kDegSmem = 1024 + kABytes + kStages * kBBytes + 256;
 
-template <int MODE, int NQ1, int NQ2>
 __global__ void __launch_bounds__(kThreads, 1)
-modularity_gram_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                       const GramParams p) {
-  constexpr int PtPad = 4 * (NQ1 + NQ2);
-  constexpr int kLBytes = MODE ? kBN * PtPad * 4 : 0;
-  constexpr int kStageBytes = (kBBytes + kLBytes + 1023) & ~1023;
-  constexpr int TS = PtPad + 1;                       // row stride of the private T accumulators
+modularity_degrees_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                          const GramParams p) {
+  if (p.nonneg && __ldg(p.nonneg)) return;            // degrees came from the closed form (see prep)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* s_a = smem;
   uint8_t* s_stage = s_a + kABytes;
-  float* s_T = reinterpret_cast<float*>(s_stage + kStages * kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_T) + (MODE ? kEpiWarps * 32 * TS * 4 : 0));
-  uint64_t* full = bars;                  // [kStages]  TMA -> MMA + epilogue
-  uint64_t* empty = bars + kStages;       // [kStages]  MMA commit + 8 epilogue warps -> TMA
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kStages * kBBytes);
+  uint64_t* full = bars;                  // [kStages]  TMA -> MMA
+  uint64_t* empty = bars + kStages;       // [kStages]  MMA commit -> TMA
   uint64_t* tfull = bars + 2 * kStages;   // [2] MMA -> epilogue
   uint64_t* tempty = tfull + 2;           // [2] epilogue -> MMA
   uint64_t* afull = tempty + 2;           // A block landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
-  float* s_red = reinterpret_cast<float*>(tmem_slot + 2);   // [8][4] block reduction scratch
+  float* s_red = reinterpret_cast<float*>(tmem_slot + 2);   // [8] block reduction scratch
 
   const int b = blockIdx.z;
   const int row_begin = __ldg(p.cu + b), row_end = __ldg(p.cu + b + 1);
@@ -174,7 +176,7 @@ modularity_gram_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
   if (warp == kEpiWarps && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], MODE ? 1 + kEpiWarps : 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
     mbar_init(afull, 1);
     mbar_fence_init();
@@ -186,7 +188,6 @@ modularity_gram_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kEpiWarps) {
-    // ------------------------------ producer ------------------------------
     if (lane == 0) {
       mbar_arrive_expect_tx(afull, kABytes);
 #pragma unroll
@@ -194,16 +195,14 @@ modularity_gram_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       for (int it = 0; it < ntiles; ++it) {
         const int stage = it % kStages;
         mbar_wait_idle(&empty[stage], ((it / kStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[stage], kBBytes + kLBytes);
-        uint8_t* dst = s_stage + (size_t)stage * kStageBytes;
+        mbar_arrive_expect_tx(&full[stage], kBBytes);
+        uint8_t* dst = s_stage + (size_t)stage * kBBytes;
         const int j0 = row_begin + (t0 + it) * kBN;
 #pragma unroll
         for (int bx = 0; bx < 4; ++bx) tma_load_2d(dst + bx * (kBN * 128), &tm_b, &full[stage], bx * 64, j0);
-        if (MODE) bulk_load(dst + kBBytes, p.lfix + (size_t)j0 * PtPad, kLBytes, &full[stage]);
       }
     }
   } else if (warp == kEpiWarps + 1) {
-    // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
       mbar_wait_idle(afull, 0);
@@ -214,7 +213,7 @@ modularity_gram_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
         mbar_wait_idle(&tempty[acc], ((it >> 1) & 1) ^ 1);
         mbar_wait_idle(&full[stage], (it / kStages) & 1);
         tc_fence_after();
-        const uint32_t sb = smem_u32(s_stage + (size_t)stage * kStageBytes);
+        const uint32_t sb = smem_u32(s_stage + (size_t)stage * kBBytes);
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k) {
           const uint64_t ad = umma_desc_sw128(sa + (k >> 2) * (kBM * 128) + (k & 3) * 32, 0, 1024);
@@ -226,30 +225,12 @@ modularity_gram_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       }
     }
   } else {
-    // ------------------------------ epilogue: thread = (row i, 32 of the 64 columns) ------------------
     const int q = warp & 3, hc = warp >> 2;
     const int i = i0 + q * 32 + lane;
     const bool row_ok = i < row_end;
-    float acc_d = 0.f;                               // MODE 0
-    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};    // MODE 1
-    int Li[MODE ? PtPad : 1];
-    float di = 0.f, k1 = 0.f, k2 = 0.f;
-    float* myT = s_T + (size_t)(warp * 32 + lane) * TS;
-    if (MODE) {
-#pragma unroll
-      for (int k = 0; k < PtPad; ++k) {
-        Li[k] = row_ok ? (__ldg(p.lfix + (size_t)i * PtPad + k) & ~31) : (kZeroFix * 32);
-        myT[k] = 0.f;
-      }
-      di = row_ok ? __ldg(p.d + i) : 0.f;
-      const double e = p.e[b];
-      k1 = (float)(1.0 / e);
-      k2 = (float)(1.0 / (e * e));
-    }
-    const float nx2scale = -2.f * 1.4426950408889634f * p.inv_temp;   // tanh(u/temp) via exp2(-2 u log2e / temp)
-    const float gscale = -200.f * p.inv_temp;                        // 2 * (-100) / temp
+    float acc_d = 0.f;
     for (int it = 0; it < ntiles; ++it) {
-      const int stage = it % kStages, acc = it & 1;
+      const int acc = it & 1;
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
       uint32_t v[32];
@@ -258,129 +239,35 @@ modularity_gram_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);      // accumulator is in registers: release TMEM early
-      const int jbase = row_begin + (t0 + it) * kBN + hc * 32;
-      if (MODE == 0) {
-        // interior tiles (no diagonal, no bag end) need no per-pair masks: relu + add only
-        const int jt0 = row_begin + (t0 + it) * kBN;
-        const bool interior = (jt0 + kBN <= row_end) && (jt0 >= i0 + kBM || jt0 + kBN <= i0);
-        if (interior) {
-          float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-          for (int jj = 0; jj < 32; jj += 2) {
-            p0 += fmaxf(__uint_as_float(v[jj]), 0.f);
-            p1 += fmaxf(__uint_as_float(v[jj + 1]), 0.f);
-          }
-          acc_d += p0 + p1;
-        } else {
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const int j = jbase + jj;
-            const float a = fmaxf(__uint_as_float(v[jj]), 0.f);
-            acc_d += (j < row_end && j != i) ? a : 0.f;
-          }
-        }
-      } else {
-        mbar_wait(&full[stage], (it / kStages) & 1);           // L tile of this stage
-        const uint8_t* st = s_stage + (size_t)stage * kStageBytes + kBBytes;
-        const int4* sL = reinterpret_cast<const int4*>(st) + (size_t)hc * 32 * (PtPad / 4);
-        const float dj_lane = (jbase + lane < row_end) ? __ldg(p.d + jbase + lane) : 0.f;
-        // Two columns per step and four independent add-max chains per token group (a dependent
-        // VIADDMNMX issues only every ~5 cycles), software-pipelined: the chains of columns jj+2,jj+3
-        // are issued before the exp2/rcp tail of columns jj,jj+1 so the MUFU latency hides behind them.
-        auto chains = [&](int jj, int (&mg0)[2], int (&mg1)[2]) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int4* lj = sL + (jj + c) * (PtPad / 4);
-            int ch[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
-#pragma unroll
-            for (int qd = 0; qd < NQ1; ++qd) {
-              const int4 w = lj[qd];
-              ch[0] = __viaddmax_s32(Li[4 * qd + 0], w.x, ch[0]);
-              ch[1] = __viaddmax_s32(Li[4 * qd + 1], w.y, ch[1]);
-              ch[2] = __viaddmax_s32(Li[4 * qd + 2], w.z, ch[2]);
-              ch[3] = __viaddmax_s32(Li[4 * qd + 3], w.w, ch[3]);
-            }
-            mg0[c] = max(__vimax3_s32(ch[0], ch[1], ch[2]), ch[3]);
-            int cg[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
-#pragma unroll
-            for (int qd = 0; qd < NQ2; ++qd) {
-              const int4 w = lj[NQ1 + qd];
-              cg[0] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 0], w.x, cg[0]);
-              cg[1] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 1], w.y, cg[1]);
-              cg[2] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 2], w.z, cg[2]);
-              cg[3] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 3], w.w, cg[3]);
-            }
-            mg1[c] = max(__vimax3_s32(cg[0], cg[1], cg[2]), cg[3]);
-          }
-        };
-        auto tail = [&](int jj, const int (&mg0)[2], const int (&mg1)[2]) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int j = jbase + jj + c;
-            const bool ok = row_ok && j < row_end;
-            const float a = (ok && j != i) ? fmaxf(__uint_as_float(v[jj + c]), 0.f) : 0.f;
-            const float djv = __shfl_sync(0xffffffffu, dj_lane, jj + c);   // warp-uniform: never under a lane predicate
-            const float dd = ok ? di * djv : 0.f;
-            const float gw4 = 4.f * gscale * (a * k1 - dd * k2);           // 0 for masked pairs
-#pragma unroll
-            for (int grp = 0; grp < (NQ2 ? 2 : 1); ++grp) {
-              const int m = grp ? mg1[c] : mg0[c];
-              const int pstar = (m & 31) + (grp ? 4 * NQ1 : 0);
-              // the 5 index bits perturb log2(u) by < 2^-16: far below the fixed-point resolution that matters
-              const float u = ex2_approx((float)m * (1.f / (float)(1 << (kLogShift + 5))));
-              const float e2 = ex2_approx(u * nx2scale);             // exp(-2u/temp)
-              const float r = rcp_approx(1.f + e2);
-              const float t1 = e2 * r;
-              const float delta = r - t1;                            // tanh(u/temp) = (1-e2)/(1+e2)
-              s1[grp] = fmaf(a, delta, s1[grp]);
-              s2[grp] = fmaf(dd, delta, s2[grp]);
-              myT[pstar] += (gw4 * t1) * (r * u);                    // 2 g (1-delta^2)/temp * u,  1-delta^2 = 4 e2 r^2
-            }
-          }
-        };
-        int ma0[2], ma1[2];
-        chains(0, ma0, ma1);
+      const int jt0 = row_begin + (t0 + it) * kBN;
+      const int jbase = jt0 + hc * 32;
+      // interior tiles (no diagonal, no bag end) need no per-pair masks: relu + add only
+      const bool interior = (jt0 + kBN <= row_end) && (jt0 >= i0 + kBM || jt0 + kBN <= i0);
+      if (interior) {
+        float p0 = 0.f, p1 = 0.f;
 #pragma unroll
         for (int jj = 0; jj < 32; jj += 2) {
-          int mb0[2] = {INT_MIN, INT_MIN}, mb1[2] = {INT_MIN, INT_MIN};
-          if (jj + 2 < 32) chains(jj + 2, mb0, mb1);
-          tail(jj, ma0, ma1);
-          ma0[0] = mb0[0]; ma0[1] = mb0[1]; ma1[0] = mb1[0]; ma1[1] = mb1[1];
+          p0 += fmaxf(__uint_as_float(v[jj]), 0.f);
+          p1 += fmaxf(__uint_as_float(v[jj + 1]), 0.f);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
+        acc_d += p0 + p1;
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const int j = jbase + jj;
+          const float a = fmaxf(__uint_as_float(v[jj]), 0.f);
+          acc_d += (j < row_end && j != i) ? a : 0.f;
+        }
       }
     }
-    // ---------------- flush ----------------
-    if (MODE == 0) {
-      if (row_ok) atomicAdd(p.d + i, acc_d);
-      float tot = warp_sum(row_ok ? acc_d : 0.f);
-      if (lane == 0) s_red[warp] = tot;
-      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
-      if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < kEpiWarps; ++w) t += (double)s_red[w];
-        atomicAdd(p.e + b, t);
-      }
-    } else {
-      if (row_ok) {
-#pragma unroll 4
-        for (int k = 0; k < PtPad; ++k) {
-          const float t = myT[k];
-          if (t != 0.f) atomicAdd(p.T + (size_t)i * PtPad + k, t);
-        }
-      }
-#pragma unroll
-      for (int grp = 0; grp < 2; ++grp) {
-        const float a1 = warp_sum(s1[grp]), a2 = warp_sum(s2[grp]);
-        if (lane == 0) { s_red[warp * 4 + grp * 2] = a1; s_red[warp * 4 + grp * 2 + 1] = a2; }
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
-      if (threadIdx.x < 4) {
-        double t = 0.0;
-        for (int w = 0; w < kEpiWarps; ++w) t += (double)s_red[w * 4 + threadIdx.x];
-        atomicAdd(p.s + (size_t)b * 4 + threadIdx.x, t);
-      }
+    if (row_ok) atomicAdd(p.d + i, acc_d);
+    float tot = warp_sum(row_ok ? acc_d : 0.f);
+    if (lane == 0) s_red[warp] = tot;
+    asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kEpiWarps; ++w) t += (double)s_red[w];
+      atomicAdd(p.e + b, t);
     }
   }
   tc_fence_before();
@@ -392,274 +279,303 @@ modularity_gram_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------
-// Symmetric pair sweep (traces + T).  Every unordered patch pair {i,j}, i <= j, is evaluated once by
-// the CTA that owns row i: CTA = 128 rows x the 32-column tiles at or right of its diagonal.
-//   thread = (row i, 16 of the 32 columns).  Row side: T_i[p*] += t in a private smem row.
-//   Column side: (t | p*) words go through a warp-private smem transpose so that lane = column owns
-//   the update T_j[p*] += t (no atomics in the loop); column accumulators are flushed to global
-//   memory per tile with one RED per non-zero entry.
+// Pair sweep (traces + T): the dominant kernel of the training step.
+//   CTA = 128 rows x a range of 64-column tiles; 16 warps, thread = (row i, 16 of the 64 columns), 128 registers
+//   per thread (a 17th warp would cap every thread at 96).  There are no dedicated producer / MMA warps: the
+//   pair work of a tile is ~3 us, so lane 0 of warp 0 issues the asynchronous work inline -- at the top of
+//   tile t the TMA loads of B(t+1) and of the L/degree tile t+2, halfway through tile t the tcgen05 MMA of
+//   tile t+1 (128x64x256 into the other TMEM buffer).  Per pair every thread runs
+//     - the (max,x) contraction over tokens as one VIADDMNMX (min form) per (pair, token) on the ALU pipe,
+//       four independent chains per token group;  the row operand carries the float "magic" offset
+//       0x4B000000, so the winning sum IS the bit pattern of the float 2^23 + n and needs no I2F;
+//     - the tanh / gradient tail on packed fp32x2 instructions (FFMA2/FMUL2) over two columns at a time;
+//     - T_i[p*] += t in a thread-private, token-major shared array (bank = thread: conflict free).
 // ------------------------------------------------------------------------------------------
-constexpr int kPN = 32;                               // columns per tile of the pair sweep
-constexpr int kPBBytes = kPN * kD * 2;                // 16 KB, four [32][64] boxes
-constexpr int kXWords = 2 * 16 * 33;                  // per warp: [group][column][row + pad]
+constexpr int kSwWarps = 16;
+constexpr int kSwEpi = kSwWarps * 32;               // 512 epilogue threads
+constexpr int kSwThreads = kSwEpi;
+constexpr int kLStages = 4;
+constexpr int kDTile = (kBN + 4) * 4;               // degree tile: 64 floats from a 16-byte aligned start
 
-template <int NQ1, int NQ2>
-constexpr size_t pairs_smem() {
-  constexpr int PtPad = 4 * (NQ1 + NQ2);
-  size_t stage = (kPBBytes + (size_t)kPN * PtPad * 4 + 1023) & ~(size_t)1023;
-  size_t t = 2 * (size_t)kEpiWarps * 32 * (PtPad + 1) * 4;
-  return 1024 + kABytes + kStages * stage + t + (size_t)kEpiWarps * kXWords * 4 + 256;
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)), "l"(*reinterpret_cast<uint64_t*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
 }
 
 template <int NQ1, int NQ2>
-__global__ void __launch_bounds__(kThreads, 1)
-modularity_pairs_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+constexpr size_t sweep_smem() {
+  constexpr int PtPad = 4 * (NQ1 + NQ2);
+  return 1024 + kABytes + kBBytes + (size_t)kLStages * (kBN * PtPad * 4 + kDTile) + (size_t)PtPad * kSwEpi * 4 + 512;
+}
+
+template <int NQ1, int NQ2>
+__global__ void __launch_bounds__(kSwThreads, 1)
+modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                         const GramParams p) {
   constexpr int PtPad = 4 * (NQ1 + NQ2);
-  constexpr int kLBytes = kPN * PtPad * 4;
-  constexpr int kStageBytes = (kPBBytes + kLBytes + 1023) & ~1023;
-  constexpr int TS = PtPad + 1;
+  constexpr int NG = NQ2 ? 2 : 1;
+  constexpr int kLBytes = kBN * PtPad * 4;
+  constexpr int kLStage = kLBytes + kDTile;             // L tile + degree tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* s_a = smem;
-  uint8_t* s_stage = s_a + kABytes;
-  float* s_Trow = reinterpret_cast<float*>(s_stage + kStages * kStageBytes);
-  float* s_Tcol = s_Trow + kEpiWarps * 32 * TS;
-  uint32_t* s_X = reinterpret_cast<uint32_t*>(s_Tcol + kEpiWarps * 32 * TS);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_X + kEpiWarps * kXWords);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kStages;
-  uint64_t* tfull = bars + 2 * kStages;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* afull = tempty + 2;
+  uint8_t* s_b = s_a + kABytes;
+  uint8_t* s_l = s_b + kBBytes;
+  float* s_T = reinterpret_cast<float*>(s_l + kLStages * kLStage);       // [PtPad][512]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_T + (size_t)PtPad * kSwEpi);
+  uint64_t* bfull = bars;                 // TMA -> MMA
+  uint64_t* bempty = bars + 1;            // MMA commit -> TMA
+  uint64_t* tfull = bars + 2;             // [2] MMA -> epilogue
+  uint64_t* tempty = bars + 4;            // [2] epilogue -> MMA
+  uint64_t* lfull = bars + 6;             // [kLStages] TMA -> epilogue
+  uint64_t* lempty = lfull + kLStages;    // [kLStages] 16 epilogue warps -> TMA
+  uint64_t* afull = lempty + kLStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
-  float* s_red = reinterpret_cast<float*>(tmem_slot + 2);
+  float* s_red = reinterpret_cast<float*>(tmem_slot + 2);                 // [16][4]
 
-  const int b = blockIdx.x, rb = blockIdx.z;          // bags vary fastest: the heavy row blocks (rb = 0) start first
+  const int b = blockIdx.z;
   const int row_begin = __ldg(p.cu + b), row_end = __ldg(p.cu + b + 1);
   const int n = row_end - row_begin;
-  const int i0 = row_begin + rb * kBM;
+  const int i0 = row_begin + blockIdx.x * kBM;
   if (i0 >= row_end) return;
-  const int ntiles_bag = (n + kPN - 1) / kPN;
-  const int t_lo = rb * (kBM / kPN);                       // first tile that touches the diagonal block
-  const int per = (ntiles_bag - t_lo + (int)gridDim.y - 1) / (int)gridDim.y;
-  const int t0 = t_lo + blockIdx.y * per;
-  const int ntiles = max(0, min(ntiles_bag, t0 + per) - t0);
+  const int ntiles_bag = (n + kBN - 1) / kBN;
+  const int t0 = blockIdx.y * p.tiles_per_split;
+  const int ntiles = max(0, min(ntiles_bag, t0 + p.tiles_per_split) - t0);
   if (ntiles == 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == kEpiWarps && lane == 0) {
+  if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + kEpiWarps); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
+    mbar_init(bfull, 1); mbar_init(bempty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kSwWarps); }
+    for (int i = 0; i < kLStages; ++i) { mbar_init(&lfull[i], 1); mbar_init(&lempty[i], kSwWarps); }
     mbar_init(afull, 1);
     mbar_fence_init();
   }
-  if (warp == kEpiWarps + 1) tmem_alloc(tmem_slot, 64);
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool driver = (warp == 0 && lane == 0);       // issues TMA and MMA for the whole CTA
 
-  if (warp == kEpiWarps) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(afull, kABytes);
+  auto load_b = [&](int it) {                          // B box of tile `it` (single stage: after the MMA of tile it-1)
+    mbar_wait(bempty, (it & 1) ^ 1);
+    mbar_arrive_expect_tx(bfull, kBBytes);
+    const int j0 = row_begin + (t0 + it) * kBN;
 #pragma unroll
-      for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_a + bx * (kBM * 128), &tm_a, afull, bx * 64, i0);
-      for (int it = 0; it < ntiles; ++it) {
-        const int stage = it % kStages;
-        mbar_wait_idle(&empty[stage], ((it / kStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[stage], kPBBytes + kLBytes);
-        uint8_t* dst = s_stage + (size_t)stage * kStageBytes;
-        const int j0 = row_begin + (t0 + it) * kPN;
+    for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_b + bx * (kBN * 128), &tm_b, bfull, bx * 64, j0);
+  };
+  auto load_l = [&](int it) {                          // L tile + degree tile of tile `it`
+    const int ls = it % kLStages;
+    mbar_wait(&lempty[ls], ((it / kLStages) & 1) ^ 1);
+    mbar_arrive_expect_tx(&lfull[ls], kLStage);
+    const int j0 = row_begin + (t0 + it) * kBN;
+    uint8_t* dst = s_l + (size_t)ls * kLStage;
+    bulk_load(dst, p.lfix + (size_t)j0 * PtPad, kLBytes, &lfull[ls]);
+    bulk_load(dst + kLBytes, p.d + (j0 & ~3), kDTile, &lfull[ls]);        // bulk copies need 16-byte aligned sources
+  };
+  auto issue_mma = [&](int it) {
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
+    const int acc = it & 1;
+    mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+    mbar_wait(bfull, it & 1);
+    tc_fence_after();
+    const uint32_t sa = smem_u32(s_a), sb = smem_u32(s_b);
 #pragma unroll
-        for (int bx = 0; bx < 4; ++bx) tma_load_2d(dst + bx * (kPN * 128), &tm_b, &full[stage], bx * 64, j0);
-        bulk_load(dst + kPBBytes, p.lfix + (size_t)j0 * PtPad, kLBytes, &full[stage]);
-      }
+    for (int k = 0; k < kD / 16; ++k) {
+      const uint64_t ad = umma_desc_sw128(sa + (k >> 2) * (kBM * 128) + (k & 3) * 32, 0, 1024);
+      const uint64_t bd = umma_desc_sw128(sb + (k >> 2) * (kBN * 128) + (k & 3) * 32, 0, 1024);
+      umma_f16(tmem_base + acc * kBN, ad, bd, idesc, k != 0);
     }
-  } else if (warp == kEpiWarps + 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, kPN, 0, 0);
-      mbar_wait_idle(afull, 0);
-      tc_fence_after();
-      const uint32_t sa = smem_u32(s_a);
-      for (int it = 0; it < ntiles; ++it) {
-        const int stage = it % kStages, acc = it & 1;
-        mbar_wait_idle(&tempty[acc], ((it >> 1) & 1) ^ 1);
-        mbar_wait_idle(&full[stage], (it / kStages) & 1);
-        tc_fence_after();
-        const uint32_t sb = smem_u32(s_stage + (size_t)stage * kStageBytes);
+    umma_commit(bempty);
+    umma_commit(&tfull[acc]);
+  };
+  if (driver) {
+    mbar_arrive_expect_tx(afull, kABytes);
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) {
-          const uint64_t ad = umma_desc_sw128(sa + (k >> 2) * (kBM * 128) + (k & 3) * 32, 0, 1024);
-          const uint64_t bd = umma_desc_sw128(sb + (k >> 2) * (kPN * 128) + (k & 3) * 32, 0, 1024);
-          umma_f16(tmem_base + acc * kPN, ad, bd, idesc, k != 0);
-        }
-        umma_commit(&empty[stage]);
-        umma_commit(&tfull[acc]);
-      }
-    }
-  } else {
+    for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_a + bx * (kBM * 128), &tm_a, afull, bx * 64, i0);
+    load_b(0);
+    load_l(0);
+    if (ntiles > 1) load_l(1);
+    mbar_wait(afull, 0);
+    issue_mma(0);
+  }
+  {
+    // ------------------------------ epilogue: thread = (row i, 16 of the 64 columns) ------------------
     const int q = warp & 3, hc = warp >> 2;
+    const int tid = threadIdx.x;                       // = hc*128 + row in block
     const int i = i0 + q * 32 + lane;
     const bool row_ok = i < row_end;
-    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
-    int Li[PtPad];
-    float* myTrow = s_Trow + (size_t)(warp * 32 + lane) * TS;
-    float* myTcol = s_Tcol + (size_t)(warp * 32 + lane) * TS;
-    uint32_t* myX = s_X + (size_t)warp * kXWords;
+    float* myT = s_T + tid;                            // element p at myT[p * 512]
+    float2 Li[PtPad / 2];                              // row operand, token pairs: 2^23 + (N_i << 5)
 #pragma unroll
-    for (int k = 0; k < PtPad; ++k) {
-      Li[k] = row_ok ? (__ldg(p.lfix + (size_t)i * PtPad + k) & ~31) : (kZeroFix * 32);
-      myTrow[k] = 0.f;
-      myTcol[k] = 0.f;
+    for (int k = 0; k < PtPad; k += 2) {
+      const float2 w = row_ok ? __ldg(reinterpret_cast<const float2*>(p.lfix + (size_t)i * PtPad + k))
+                              : make_float2((float)(kNMax << 5), (float)(kNMax << 5));
+      Li[k >> 1] = make_float2((float)((int)w.x & ~31) + 8388608.f, (float)((int)w.y & ~31) + 8388608.f);
+      myT[k * kSwEpi] = 0.f;
+      myT[(k + 1) * kSwEpi] = 0.f;
     }
     const float di = row_ok ? __ldg(p.d + i) : 0.f;
     const double e = p.e[b];
     const float k1 = (float)(1.0 / e), k2 = (float)(1.0 / (e * e));
-    const float nx2scale = -2.f * 1.4426950408889634f * p.inv_temp;
-    const float gscale4 = -800.f * p.inv_temp;                          // 4 * 2 * (-100) / temp
-    const int cx = lane & 15, hx = lane >> 4;                           // column-phase role of this lane
+    const float gs4 = -800.f * p.inv_temp;                                 // 4 * 2 * (-100) / temp
+    const float2 c0 = make_float2(gs4 * k1, gs4 * k1);
+    const float2 nci = make_float2(-gs4 * k2 * di, -gs4 * k2 * di);
+    const float nx2 = -2.f * 1.4426950408889634f * p.inv_temp;             // tanh(u/temp) via exp2(-2 u log2e / temp)
+    const float2 nx2s = make_float2(nx2, nx2);
+    const float2 kscale = make_float2(-1.f / (float)(1 << (kLogShift + 5)), -1.f / (float)(1 << (kLogShift + 5)));
+    const float2 koff = make_float2(kArgOff, kArgOff);
+    const float2 one2 = make_float2(1.f, 1.f), neg2 = make_float2(-1.f, -1.f);
+    float2 sg[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+
     for (int it = 0; it < ntiles; ++it) {
-      const int stage = it % kStages, acc = it & 1;
+      const int acc = it & 1, ls = it % kLStages;
+      if (driver) {
+        if (it + 1 < ntiles) load_b(it + 1);
+        if (it + 2 < ntiles) load_l(it + 2);
+      }
+      __syncwarp();
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kPN + hc * 16, v);
+      uint32_t v[8];                                     // columns 0-7 now, 8-15 halfway through the tile
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kBN + hc * 16;
+      tmem_ld8(taddr, v);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      const int jbase = row_begin + (t0 + it) * kPN + hc * 16;
-      mbar_wait(&full[stage], (it / kStages) & 1);
-      const uint8_t* st = s_stage + (size_t)stage * kStageBytes + kPBBytes;
-      const int4* sL = reinterpret_cast<const int4*>(st) + (size_t)hc * 16 * (PtPad / 4);
-      const float dj_lane = (jbase + cx < row_end) ? __ldg(p.d + jbase + cx) : 0.f;
+      mbar_wait(&lfull[ls], (it / kLStages) & 1);
+      const uint8_t* st = s_l + (size_t)ls * kLStage;
+      const float4* sL = reinterpret_cast<const float4*>(st) + (size_t)hc * 16 * (PtPad / 4);
+      const int jt0 = row_begin + (t0 + it) * kBN;
+      const float* sd = reinterpret_cast<const float*>(st + kLBytes) + (jt0 & 3) + hc * 16;
+      const int jbase = jt0 + hc * 16;
+      const bool interior = (i0 + kBM <= row_end) && (jt0 + kBN <= row_end) && (jt0 >= i0 + kBM || jt0 + kBN <= i0);
 
-      auto chains = [&](int jj, int (&mg0)[2], int (&mg1)[2]) {
+      // (min,+) contraction over tokens: one packed FADD2 (FMA pipe) per token PAIR, one 3-input FMNMX3
+      // (ALU pipe) folding both sums into one of four independent chains per token group
+      auto chains = [&](int jj, int (&m)[2][2]) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const int4* lj = sL + (jj + c) * (PtPad / 4);
-          int ch[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
+          const float4* lj = sL + (jj + c) * (PtPad / 4);
+          float ch[4] = {3e38f, 3e38f, 3e38f, 3e38f};
 #pragma unroll
           for (int qd = 0; qd < NQ1; ++qd) {
-            const int4 w = lj[qd];
-            ch[0] = __viaddmax_s32(Li[4 * qd + 0], w.x, ch[0]);
-            ch[1] = __viaddmax_s32(Li[4 * qd + 1], w.y, ch[1]);
-            ch[2] = __viaddmax_s32(Li[4 * qd + 2], w.z, ch[2]);
-            ch[3] = __viaddmax_s32(Li[4 * qd + 3], w.w, ch[3]);
+            const float4 w = lj[qd];
+            const float2 sa = add2(Li[2 * qd], make_float2(w.x, w.y));
+            const float2 sb = add2(Li[2 * qd + 1], make_float2(w.z, w.w));
+            ch[(2 * qd) & 3] = fminf(fminf(sa.x, sa.y), ch[(2 * qd) & 3]);
+            ch[(2 * qd + 1) & 3] = fminf(fminf(sb.x, sb.y), ch[(2 * qd + 1) & 3]);
           }
-          mg0[c] = max(__vimax3_s32(ch[0], ch[1], ch[2]), ch[3]);
-          int cg[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
+          m[c][0] = __float_as_int(fminf(fminf(ch[0], ch[1]), fminf(ch[2], ch[3])));
+          float cg[4] = {3e38f, 3e38f, 3e38f, 3e38f};
 #pragma unroll
           for (int qd = 0; qd < NQ2; ++qd) {
-            const int4 w = lj[NQ1 + qd];
-            cg[0] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 0], w.x, cg[0]);
-            cg[1] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 1], w.y, cg[1]);
-            cg[2] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 2], w.z, cg[2]);
-            cg[3] = __viaddmax_s32(Li[4 * (NQ1 + qd) + 3], w.w, cg[3]);
+            const float4 w = lj[NQ1 + qd];
+            const float2 sa = add2(Li[2 * (NQ1 + qd)], make_float2(w.x, w.y));
+            const float2 sb = add2(Li[2 * (NQ1 + qd) + 1], make_float2(w.z, w.w));
+            cg[(2 * qd) & 3] = fminf(fminf(sa.x, sa.y), cg[(2 * qd) & 3]);
+            cg[(2 * qd + 1) & 3] = fminf(fminf(sb.x, sb.y), cg[(2 * qd + 1) & 3]);
           }
-          mg1[c] = max(__vimax3_s32(cg[0], cg[1], cg[2]), cg[3]);
+          m[c][1] = NQ2 ? __float_as_int(fminf(fminf(cg[0], cg[1]), fminf(cg[2], cg[3]))) : 0;
         }
       };
-      auto tail = [&](int jj, const int (&mg0)[2], const int (&mg1)[2]) {
+      auto tail = [&](int jj, const int (&m)[2][2], auto interior_tag) {
+        constexpr bool INTERIOR = decltype(interior_tag)::value;
+        float2 a2 = make_float2(fmaxf(__uint_as_float(v[jj & 7]), 0.f), fmaxf(__uint_as_float(v[(jj & 7) + 1]), 0.f));
+        float2 dj2 = make_float2(sd[jj], sd[jj + 1]);
+        if (!INTERIOR) {
+          const int j = jbase + jj;
+          const bool ok0 = row_ok && j < row_end, ok1 = row_ok && j + 1 < row_end;
+          a2.x = (ok0 && j != i) ? a2.x : 0.f;
+          a2.y = (ok1 && j + 1 != i) ? a2.y : 0.f;
+          dj2.x = ok0 ? dj2.x : 0.f;
+          dj2.y = ok1 ? dj2.y : 0.f;
+        }
+        const float2 gw = fma2(a2, c0, mul2(dj2, nci));                 // 4*2*(-100)/temp * (A/e - d_i d_j/e^2); 0 when masked
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int j = jbase + jj + c;
-          const bool ok = row_ok && j < row_end && j >= i;                 // upper triangle + diagonal only
-          const float sym = j > i ? 2.f : 1.f;                             // an unordered pair stands for (i,j) and (j,i)
-          const float a = (ok && j != i) ? fmaxf(__uint_as_float(v[jj + c]), 0.f) : 0.f;
-          const float djv = __shfl_sync(0xffffffffu, dj_lane, jj + c);     // warp-uniform: never under a lane predicate
-          const float dd = ok ? di * djv : 0.f;
-          const float gw4 = gscale4 * (a * k1 - dd * k2);                  // 0 for masked pairs
-          const float as = a * sym, ds = dd * sym;
+        for (int grp = 0; grp < NG; ++grp) {
+          const int m0 = m[0][grp], m1 = m[1][grp];
+          const int pl0 = m0 & 31, pl1 = m1 & 31;
+          const float2 F = make_float2(__int_as_float(m0 & ~31), __int_as_float(m1 & ~31));
+          const float2 arg = fma2(F, kscale, koff);                     // log2(C_i C_j) of the winning token
+          float2 u = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
+          const float2 x = mul2(u, nx2s);
+          const float2 e2 = make_float2(ex2_approx(x.x), ex2_approx(x.y));   // exp(-2u/temp)
+          const float2 den = add2(e2, one2);
+          const float2 r = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+          const float2 t1 = mul2(e2, r);
+          const float2 delta = fma2(t1, neg2, r);                       // tanh(u/temp) = (1-e2)/(1+e2)
+          sg[grp] = fma2(gw, delta, sg[grp]);                           // sum of gs4 * (A/e - d_i d_j/e^2) * delta
+          const float2 t = mul2(mul2(gw, t1), mul2(r, u));              // 2 g (1-delta^2)/temp * u, 1-delta^2 = 4 e2 r^2
+          float* T0 = myT + (size_t)(pl0 + (grp ? 4 * NQ1 : 0)) * kSwEpi;
+          *T0 += t.x;
+          float* T1 = myT + (size_t)(pl1 + (grp ? 4 * NQ1 : 0)) * kSwEpi;
+          *T1 += t.y;
+        }
+      };
+      auto sweep = [&](auto interior_tag) {
 #pragma unroll
-          for (int grp = 0; grp < (NQ2 ? 2 : 1); ++grp) {
-            const int m = grp ? mg1[c] : mg0[c];
-            const int pl = m & 31;
-            const float u = ex2_approx((float)m * (1.f / (float)(1 << (kLogShift + 5))));
-            const float e2 = ex2_approx(u * nx2scale);
-            const float r = rcp_approx(1.f + e2);
-            const float t1 = e2 * r;
-            const float delta = r - t1;
-            s1[grp] = fmaf(as, delta, s1[grp]);
-            s2[grp] = fmaf(ds, delta, s2[grp]);
-            const float t = (gw4 * t1) * (r * u);
-            myTrow[pl + (grp ? 4 * NQ1 : 0)] += t;
-            // column side: (t | p*) to the transpose buffer; the diagonal pair has no mirror image
-            const uint32_t word = j > i ? ((__float_as_uint(t) & ~31u) | (uint32_t)pl) : (uint32_t)pl;
-            myX[(grp * 16 + jj + c) * 33 + lane] = word;
+        for (int jj = 0; jj < 16; jj += 2) {
+          int m[2][2];
+          chains(jj, m);
+          tail(jj, m, interior_tag);
+          if (jj == 6) {                                 // second half of the accumulator row, then release the TMEM buffer
+            tmem_ld8(taddr + 8, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (driver && it + 1 < ntiles) issue_mma(it + 1);
+            __syncwarp();
           }
         }
       };
-      int ma0[2], ma1[2];
-      chains(0, ma0, ma1);
-#pragma unroll
-      for (int jj = 0; jj < 16; jj += 2) {
-        int mb0[2] = {INT_MIN, INT_MIN}, mb1[2] = {INT_MIN, INT_MIN};
-        if (jj + 2 < 16) chains(jj + 2, mb0, mb1);
-        tail(jj, ma0, ma1);
-        ma0[0] = mb0[0]; ma0[1] = mb0[1]; ma1[0] = mb1[0]; ma1[1] = mb1[1];
-      }
+      if (interior) sweep(std::true_type{}); else sweep(std::false_type{});
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stage]);
-      // ---- column phase: lane (cx, hx) folds rows hx*16..+15 of column cx into its private accumulators ----
-#pragma unroll
-      for (int grp = 0; grp < (NQ2 ? 2 : 1); ++grp) {
-        const uint32_t* col = myX + (grp * 16 + cx) * 33 + hx * 16;
-#pragma unroll 4
-        for (int r = 0; r < 16; ++r) {
-          const uint32_t w = col[r];
-          myTcol[(w & 31u) + (grp ? 4 * NQ1 : 0)] += __uint_as_float(w & ~31u);
-        }
-      }
-      // ---- combine the 8 partial accumulators of every column inside the CTA, one RED per non-zero ----
-      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
-      {
-        const int jt0 = row_begin + (t0 + it) * kPN;
-        for (int ent = threadIdx.x; ent < kPN * PtPad; ent += kEpiWarps * 32) {
-          const int c32 = ent / PtPad, k = ent - c32 * PtPad;
-          float* base = s_Tcol + (size_t)(((c32 >> 4) * 4) * 32 + (c32 & 15)) * TS + k;   // warp (hc*4+q), lane hx*16+cx
-          float tsum = 0.f;
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq)
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              float* ptr = base + (size_t)(qq * 32 + hh * 16) * TS;
-              tsum += *ptr;
-              *ptr = 0.f;
-            }
-          if (tsum != 0.f && jt0 + c32 < row_end) atomicAdd(p.T + (size_t)(jt0 + c32) * PtPad + k, tsum);
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
-      __syncwarp();                                   // X is rewritten by the next tile
+      if (lane == 0) mbar_arrive(&lempty[ls]);
     }
-    if (row_ok) {
-#pragma unroll 4
-      for (int k = 0; k < PtPad; ++k) {
-        const float t = myTrow[k];
-        if (t != 0.f) atomicAdd(p.T + (size_t)i * PtPad + k, t);
+    // ---------------- flush ----------------
+    {
+      const float inv_gs4 = 1.f / gs4;
+#pragma unroll
+      for (int grp = 0; grp < 2; ++grp) {
+        const float a1 = warp_sum((sg[grp].x + sg[grp].y) * inv_gs4);   // = sum A delta / e - sum d_i d_j delta / e^2
+        if (lane == 0) s_red[warp * 2 + grp] = a1;
       }
     }
-#pragma unroll
-    for (int grp = 0; grp < 2; ++grp) {
-      const float a1 = warp_sum(s1[grp]), a2 = warp_sum(s2[grp]);
-      if (lane == 0) { s_red[warp * 4 + grp * 2] = a1; s_red[warp * 4 + grp * 2 + 1] = a2; }
-    }
-    asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
-    if (threadIdx.x < 4) {
+    asm volatile("bar.sync 1, %0;" ::"r"(kSwEpi) : "memory");
+    if (tid < 2) {
       double t = 0.0;
-      for (int w = 0; w < kEpiWarps; ++w) t += (double)s_red[w * 4 + threadIdx.x];
-      atomicAdd(p.s + (size_t)b * 4 + threadIdx.x, t);
+      for (int w = 0; w < kSwWarps; ++w) t += (double)s_red[w * 2 + tid];
+      atomicAdd(p.s + (size_t)b * 2 + tid, t);
+    }
+    // the four column-quarter threads of a row are combined before one RED per (row, token)
+    for (int idx = tid; idx < kBM * PtPad; idx += kSwEpi) {
+      const int r = idx & (kBM - 1), k = idx >> 7;
+      const float* src = s_T + (size_t)k * kSwEpi + r;
+      const float t = (src[0] + src[kBM]) + (src[2 * kBM] + src[3 * kBM]);
+      if (t != 0.f && i0 + r < row_end) atomicAdd(p.T + (size_t)(i0 + r) * PtPad + k, t);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kEpiWarps + 1) {
+  if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, 128);
   }
 }
 
@@ -670,7 +586,7 @@ modularity_pairs_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
 struct FinishParams {
   const bf16* h;
   const float* invn;
-  const int* lfix;
+  const float* lfix;
   const float* T;
   const int* cu;
   const double* s;
@@ -687,9 +603,7 @@ __global__ void __launch_bounds__(256) modularity_finish_kernel(const FinishPara
   const int row_begin = __ldg(p.cu + b), row_end = __ldg(p.cu + b + 1);
   const int Pt = p.P1 + p.P2;
   if (blockIdx.x == 0 && f < 2) {
-    const double e = p.e[b];
-    const double s1 = p.s[(size_t)b * 4 + f * 2], s2 = p.s[(size_t)b * 4 + f * 2 + 1];
-    p.loss[b * 2 + f] = (float)(-100.0 * (s1 / e - s2 / (e * e)));          // utils.py:222-228
+    p.loss[b * 2 + f] = (float)(-100.0 * p.s[(size_t)b * 2 + f]);          // utils.py:222-228: -100 tr((W/e) delta)
   }
   const int r0 = row_begin + blockIdx.x * p.rows_per_cta;
   const int r1 = min(row_end, r0 + p.rows_per_cta);
@@ -707,8 +621,9 @@ __global__ void __launch_bounds__(256) modularity_finish_kernel(const FinishPara
         const size_t o = (size_t)(rb + r) * PTPAD + k;
         const float t = p.T[o];
         if (t != 0.f) {
-          const float c = ex2_approx((float)(p.lfix[o] >> 5) * (1.f / (float)(1 << kLogShift)));
-          v = c > 0.f ? t / c : 0.f;                   // relu gate: C == 0 never wins the max with u > 0
+          const int nfix = (int)p.lfix[o] >> 5;
+          const float c = ex2_approx((float)kCOff - (float)nfix * (1.f / (float)(1 << kLogShift)));
+          v = nfix < kNMax ? t / c : 0.f;              // relu gate: C == 0 never wins the max with u > 0
         }
       }
       s_dc[r][k] = v;
@@ -733,34 +648,31 @@ int pad4(int v) { return (v + 3) & ~3; }
 int quads1(int P1) { return P1 <= 8 ? 2 : (P1 <= 16 ? 4 : 8); }
 int quads2(int P2) { return P2 == 0 ? 0 : (P2 <= 8 ? 2 : (P2 <= 16 ? 4 : 8)); }
 
-template <int MODE, int NQ1, int NQ2>
-int run_gram(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p, dim3 grid, cudaStream_t st) {
-  constexpr size_t smem = gram_smem<MODE, NQ1, NQ2>();
-  static_assert(smem <= 227 * 1024, "modularity_gram shared memory");
+int run_degrees(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p, dim3 grid, cudaStream_t st) {
   static bool done = false;
   if (!done) {
-    IMP_CUDA(cudaFuncSetAttribute(modularity_gram_kernel<MODE, NQ1, NQ2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IMP_CUDA(cudaFuncSetAttribute(modularity_degrees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDegSmem));
     done = true;
   }
-  IMP_LAUNCH(MODE ? "modularity_gram_main" : "modularity_gram_degrees", st, modularity_gram_kernel<MODE, NQ1, NQ2><<<grid, kThreads, smem, st>>>(ta, tb, p));
+  IMP_LAUNCH("modularity_gram_degrees", st, modularity_degrees_kernel<<<grid, kThreads, kDegSmem, st>>>(ta, tb, p));
   return IMP_OK;
 }
 
 template <int NQ1, int NQ2>
-int run_pairs(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p, dim3 grid, cudaStream_t st) {
-  constexpr size_t smem = pairs_smem<NQ1, NQ2>();
-  static_assert(smem <= 227 * 1024, "modularity_pairs shared memory");
+int run_sweep(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = sweep_smem<NQ1, NQ2>();
+  static_assert(smem <= 227 * 1024, "modularity_sweep shared memory");
   static bool done = false;
   if (!done) {
-    IMP_CUDA(cudaFuncSetAttribute(modularity_pairs_kernel<NQ1, NQ2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IMP_CUDA(cudaFuncSetAttribute(modularity_sweep_kernel<NQ1, NQ2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done = true;
   }
-  IMP_LAUNCH("modularity_pairs", st, modularity_pairs_kernel<NQ1, NQ2><<<grid, kThreads, smem, st>>>(ta, tb, p));
+  IMP_LAUNCH("modularity_sweep", st, modularity_sweep_kernel<NQ1, NQ2><<<grid, kSwThreads, smem, st>>>(ta, tb, p));
   return IMP_OK;
 }
 
 struct Carve {
-  bf16* xh; float* invn; int* lfix; float* d; float* T; double* e; double* s;
+  bf16* xh; float* invn; float* lfix; float* d; float* T; double* e; double* s;
   size_t zero_off, zero_bytes, total;
 };
 Carve carve(void* ws, int total_rows, int B, int PtPad) {
@@ -771,12 +683,12 @@ Carve carve(void* ws, int total_rows, int B, int PtPad) {
   Carve c;
   c.xh = reinterpret_cast<bf16*>(base + off); off += up(rpad * kD * 2);
   c.invn = reinterpret_cast<float*>(base + off); off += up(rpad * 4);
-  c.lfix = reinterpret_cast<int*>(base + off); off += up(rpad * PtPad * 4);
+  c.lfix = reinterpret_cast<float*>(base + off); off += up(rpad * PtPad * 4);
   c.zero_off = off;
   c.d = reinterpret_cast<float*>(base + off); off += up(rpad * 4);
   c.T = reinterpret_cast<float*>(base + off); off += up(rpad * PtPad * 4);
   c.e = reinterpret_cast<double*>(base + off); off += up((size_t)B * 8);
-  c.s = reinterpret_cast<double*>(base + off); off += up((size_t)B * 4 * 8);
+  c.s = reinterpret_cast<double*>(base + off); off += up((size_t)B * 2 * 8);
   c.zero_bytes = off - c.zero_off;
   c.total = off;
   return c;
@@ -831,18 +743,13 @@ int launch_modularity(const bf16* h, int total_rows, const int* cu, int B, int m
   gp.tiles_per_split = (col_tiles + nsplit - 1) / nsplit;
   nsplit = (col_tiles + gp.tiles_per_split - 1) / gp.tiles_per_split;
   const dim3 grid(row_blocks, nsplit, B);
-  if ((rc = run_gram<0, 2, 0>(ta, tb, gp, grid, st))) return rc;
-  CUtensorMap tp;
-  if ((rc = imp_make_tmap_2d(&tp, c.xh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, rpad, kD * 2, 64, kPN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  // pair sweep: triangular work per row block; split the column range so that >= 2 waves of CTAs exist
-  int psplit = std::max(1, std::min((2 * imp_num_sms() + row_blocks * B - 1) / (row_blocks * B), std::max(1, col_tiles / 8)));
-  const dim3 pgrid(B, psplit, row_blocks);
-  static const bool symmetric = []() { const char* e = getenv("IMP_MODULARITY_SYMMETRIC"); return e ? atoi(e) != 0 : false; }();   // measured on B200: the full sweep is (slightly) faster, see DESIGN.md 5
-#define IMP_GRAM(a, b2) rc = symmetric ? run_pairs<a, b2>(ta, tp, gp, pgrid, st) : run_gram<1, a, b2>(ta, tb, gp, grid, st)
-  if (nq2 == 0) { if (nq1 == 2) IMP_GRAM(2, 0); else if (nq1 == 4) IMP_GRAM(4, 0); else IMP_GRAM(8, 0); }
-  else if (nq2 == 2) { if (nq1 == 2) IMP_GRAM(2, 2); else if (nq1 == 4) IMP_GRAM(4, 2); else IMP_GRAM(8, 2); }
+  gp.nonneg = nullptr;
+  if ((rc = run_degrees(ta, tb, gp, grid, st))) return rc;
+#define IMP_SWEEP(a, b2) rc = run_sweep<a, b2>(ta, tb, gp, grid, st)
+  if (nq2 == 0) { if (nq1 == 2) IMP_SWEEP(2, 0); else if (nq1 == 4) IMP_SWEEP(4, 0); else IMP_SWEEP(8, 0); }
+  else if (nq2 == 2) { if (nq1 == 2) IMP_SWEEP(2, 2); else if (nq1 == 4) IMP_SWEEP(4, 2); else IMP_SWEEP(8, 2); }
   else IMP_FAIL(IMP_ERR_ARG, "modularity: second token group supports at most 8 tokens (got %d)", P2);
-#undef IMP_GRAM
+#undef IMP_SWEEP
   if (rc) return rc;
 
   FinishParams fp;

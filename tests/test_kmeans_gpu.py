@@ -1,7 +1,8 @@
 """A9 k-means assignment: exact int32 agreement with the oracle on ties-free fp32 inputs.
-Ties-free is made explicit: rows whose fp64 best/second-best gap is below 1e-3 (fp32 rounding of a
-~1e3-sized distance is ~1e-4) are allowed to differ, every other row must match exactly; in all
-cases the chosen centroid must be optimal within 1e-3 in fp64."""
+Ties-free is made explicit: rows whose fp64 best/second-best gap is below the fp32 rounding scale of
+the distance formula, tol = 1e-6 * (|x|^2 + max|mu|^2) (= 1e-3 for ~1e3-sized distances), are allowed
+to differ, every other row must match exactly; in all cases the chosen centroid must be optimal
+within tol in fp64."""
 import pytest
 import torch
 
@@ -14,12 +15,13 @@ def _check(x, mu, assign):
     d64 = torch.cdist(x.double(), mu.double()) ** 2
     srt = d64.sort(dim=1).values
     gap = srt[:, 1] - srt[:, 0] if mu.shape[0] > 1 else torch.full((x.shape[0],), 1.0)
-    clear = gap > 1e-3
+    tol = 1e-6 * ((x.double() ** 2).sum(1) + (mu.double() ** 2).sum(1).max())
+    clear = gap > tol
     a = assign.cpu()
     assert torch.equal(a[clear], ref[clear])
     assert clear.float().mean().item() > 0.999
     chosen = d64.gather(1, a.long()[:, None])[:, 0]
-    assert (chosen - srt[:, 0]).max().item() <= 1e-3
+    assert ((chosen - srt[:, 0]) <= tol).all().item()
     return (a == ref).float().mean().item()
 
 
@@ -62,4 +64,5 @@ def test_kmeans_update_and_fit():
     inertia0 = (torch.cdist(x, mu0) ** 2).min(dim=1).values.sum().item()
     inertia1 = (torch.cdist(x, mu.cpu()) ** 2).min(dim=1).values.sum().item()
     assert inertia1 <= inertia0 * (1 + 1e-6)
-    assert torch.equal(a2.cpu(), O.kmeans_assign(x, mu.cpu()))
+    # (exact on every row whose fp64 best/second gap is clear, optimal within 1e-3 everywhere: same rule as above)
+    _check(x, mu.cpu(), a2)
