@@ -256,8 +256,7 @@ def run_ours(args):
         "pathnet_fwd": ("hbm", rows * D_IN * 2.0), "pathnet_dw": ("hbm", rows * D_IN * 2.0),
         "pool_fwd": ("hbm", rows * 256 * 2.0), "pool_bwd_dq": ("hbm", rows * 256 * 2.0),
         "pool_bwd_dz": ("hbm", rows * 256 * 2.0 * 2),
-        "modularity_gram_degrees": ("tensor", 2.0 * B * N * N * 256), "modularity_gram_main": ("tensor", 2.0 * B * N * N * 256),
-        "modularity_pairs": ("tensor", 1.0 * B * N * N * 256),
+        "modularity_degrees_gram": ("tensor", 2.0 * B * N * N * 256), "modularity_sweep": ("tensor", 2.0 * B * N * N * 256),
     }
     kernels_out = []
     tot_kernel_ms = sum(v["ms_per_step"] for v in pk.values()) or 1.0

@@ -10,14 +10,16 @@
 // The reference materialises P x N x N and an N^3 matmul; here nothing larger than N x P is stored.
 //
 // Kernels:
-//   prep     : inv-norms, xh (bf16, the Gram operand) and L = fixed-point log2(C) per (patch, token)
-//   gram<0>  : degrees d, e       (tcgen05 Gram tiles 128 x 64, K = 256, accumulators in TMEM)
-//   gram<1>  : the two traces and T_ip = sum_j 2 g_ij (1-delta^2)/temp u_ij [p = argmax]
-//              The (max,x) contraction over tokens runs on the integer pipe in the log domain:
-//              max_p (L_ip + L_jp) with the token index carried in the 5 low bits (one
-//              add-max instruction per (pair, token)), u = exp2(max).
-//   finish   : dC = T / C, dchat_p = sum_i dC_ip xh_i, loss per token group
-// Up to two token groups (<= 32 tokens each) share A, d and e (the reference evaluates the
+//   prep            : per 64-row tile: inv-norms, xh (bf16, the Gram operand), C = xh . chat (fp32 register-tiled
+//                     FMA) as fixed-point log2 in the tiled layout the sweep streams, column sums of xh, sign flag
+//   degrees_closed  : all features >= 0 (always true behind path_net's ReLU): relu is the identity on the Gram
+//                     matrix, so d_i = xh_i . (sum_j xh_j) - xh_i . xh_i  -- O(N D) instead of an N x N sweep
+//   degrees (Gram)  : general signed features: tcgen05 Gram tiles 128 x 64 (K = 256), relu + row sums
+//   sweep           : the trace and T_ip = sum_j 2 g_ij (1-delta^2)/temp u_ij [p = argmax]; Gram tiles on tcgen05,
+//                     the (max,x) contraction over tokens in the log domain as a (min,+) contraction of
+//                     integer-valued floats: FADD2 + FMNMX3 per token pair, arg-min in the low mantissa bits
+//   finish          : dC = T / C, dchat_p = sum_i dC_ip xh_i, loss per token group
+// Up to two token groups (<= 32 and <= 8 tokens) share A, d and e (the reference evaluates the
 // prototype tokens and the omic tokens against the same bag, umeml_gan.py:520-521).
 #include "common.cuh"
 #include "launchers.h"
@@ -39,13 +41,17 @@ constexpr int kStages = 2;
 // Fixed-point log-assignments: N = round((kCOff - log2 C) * 2^kLogShift) in [0, kNMax]  (C <= 2^kCOff = 16 by
 // Cauchy-Schwarz: |xh| = 1, |chat_p| <= sqrt(256)); C == 0 (or below 2^-28) is kNMax.  Both operands are stored
 // as integer-valued FLOATS: the column operand is (N << 5) | token index, the row operand 2^23 + (N << 5).  Their
-// fp32 sum is exact (an integer below 2^24) and its bit pattern is kMagic + ((N_i + N_j) << 5 | p): the minimum
+// fp32 sum is exact (an integer below 2^24) whose bit pattern is 0x4B000000 + ((N_i + N_j) << 5 | p): the minimum
 // over tokens yields the winning log-product and the arg-min in one word, with no int<->float conversion.
+// Layout of the column operand in HBM ("tiled"): [absolute 64-row tile][token slot][64 rows], so that one bulk
+// copy brings a tile in the order the sweep reads it: for one token, 4 consecutive columns per 128-bit load.
 constexpr int kLogShift = 12;
 constexpr int kNMax = (1 << 17) - 1;
 constexpr int kCOff = 4;
-constexpr int kMagic = 0x4B000000;
 constexpr float kArgOff = 64.f + 2.f * kCOff;   // undoes 2^23 * 2^-(kLogShift+5) and the two offsets
+__host__ __device__ __forceinline__ size_t lfix_index(int row, int slot, int PtPad) {
+  return ((size_t)(row >> 6) * PtPad + slot) * 64 + (row & 63);
+}
 
 // pointer arithmetic (not an integer round trip) so the compiler keeps the shared address space
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
@@ -66,9 +72,50 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// non-blocking mbarrier probe
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)), "l"(*reinterpret_cast<uint64_t*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
 
 // ------------------------------------------------------------------------------------------
-// prep: one warp per patch row
+// prep: CTA = one absolute 64-row tile, 256 threads.
+//   phase A  warp per row: norm, xh (bf16) and inv-norm to HBM, normalised fp32 row to smem, sign flag
+//   phase B  per bag intersecting the tile: tokens to smem, C = xs . chat^T with a 2-row x TPG-token register
+//            tile per thread (K = 256 in float4 steps), fixed-point log2 into the tiled layout; column sums of
+//            the bf16-rounded xh per bag (closed-form degrees)
 // ------------------------------------------------------------------------------------------
 struct PrepParams {
   const bf16* h;            // (R,256)
@@ -76,53 +123,180 @@ struct PrepParams {
   const float* chat;        // (B, Pt, 256): tokens normalised across tokens per feature
   bf16* xh;                 // (Rpad,256)
   float* invn;              // (Rpad)
-  float* lfix;              // (Rpad, PtPad) integer-valued floats
-  int B, P1, P2, P1pad, PtPad;
+  float* lfix;              // tiled, see lfix_index
+  float* colsum;            // (B,256)  sum_j xh_j (bf16-rounded values)
+  int* negflag;             // (1) set to 1 when any element of h is negative
+  int R, B, P1, P2, P1pad;
 };
+constexpr int kXsStride = kD + 4;        // fp32 row stride in smem: 16-byte skew per row (conflict-free float4 reads)
 
+template <int PTPAD>
+constexpr size_t prep_smem() { return (size_t)(64 + PTPAD) * kXsStride * 4; }
+
+template <int PTPAD>
 __global__ void __launch_bounds__(256) modularity_prep_kernel(const PrepParams p) {
-  extern __shared__ float s_c[];                 // (PtPad, 256) fp32, zero rows for padding
-  const int b = blockIdx.y;
-  const int row_begin = __ldg(p.cu + b), row_end = __ldg(p.cu + b + 1);
-  const int Pt = p.P1 + p.P2;
-  for (int i = threadIdx.x; i < p.PtPad * kD; i += blockDim.x) {
-    const int slot = i / kD, f = i % kD;
-    int src = -1;
-    if (slot < p.P1) src = slot;
-    else if (slot >= p.P1pad && slot - p.P1pad < p.P2) src = p.P1 + slot - p.P1pad;
-    s_c[i] = src >= 0 ? p.chat[((size_t)b * Pt + src) * kD + f] : 0.f;
-  }
-  __syncthreads();
+  constexpr int TPG = PTPAD / 8;                  // token slots per thread
+  extern __shared__ float s_prep[];
+  float* xs = s_prep;                             // [64][kXsStride]
+  float* cs = xs + 64 * kXsStride;                // [PTPAD][kXsStride]
+  const int r0 = blockIdx.x * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int row = row_begin + blockIdx.x * 8 + warp; row < row_end; row += gridDim.x * 8) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(p.h + (size_t)row * kD + lane * 8);
-    float v[8] = {bf16lo(raw.x), bf16hi(raw.x), bf16lo(raw.y), bf16hi(raw.y),
-                  bf16lo(raw.z), bf16hi(raw.z), bf16lo(raw.w), bf16hi(raw.w)};
+  // ---------------- phase A ----------------
+  bool neg = false;
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    const int rl = warp * 8 + rr, row = r0 + rl;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (row < p.R) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(p.h + (size_t)row * kD + lane * 8);
+      v[0] = bf16lo(raw.x); v[1] = bf16hi(raw.x); v[2] = bf16lo(raw.y); v[3] = bf16hi(raw.y);
+      v[4] = bf16lo(raw.z); v[5] = bf16hi(raw.z); v[6] = bf16lo(raw.w); v[7] = bf16hi(raw.w);
+    }
     float ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) ss += v[k] * v[k];
+    for (int k = 0; k < 8; ++k) { ss += v[k] * v[k]; neg |= v[k] < 0.f; }
     ss = warp_sum(ss);
     const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);          // F.normalize eps (utils.py:179,193)
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] *= inv;
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(p.xh + (size_t)row * kD + lane * 8) = o;
-    if (lane == 0) p.invn[row] = inv;
-    for (int slot = 0; slot < p.PtPad; ++slot) {
-      const float4 c0 = *reinterpret_cast<const float4*>(s_c + slot * kD + lane * 8);
-      const float4 c1 = *reinterpret_cast<const float4*>(s_c + slot * kD + lane * 8 + 4);
-      float dot = v[0] * c0.x + v[1] * c0.y + v[2] * c0.z + v[3] * c0.w + v[4] * c1.x + v[5] * c1.y + v[6] * c1.z + v[7] * c1.w;
-      dot = warp_sum(dot);
-      if (lane == 0) {
-        const bool real = slot < p.P1 || (slot >= p.P1pad && slot - p.P1pad < p.P2);
-        int fix = kNMax;
-        if (real && dot > 0.f) fix = min(kNMax, max(0, __float2int_rn(((float)kCOff - log2f(dot)) * (float)(1 << kLogShift))));
-        // low 5 bits: token index inside its group (column-side operand); the row side masks them off
-        p.lfix[(size_t)row * p.PtPad + slot] = (float)(fix * 32 + (slot < p.P1pad ? slot : slot - p.P1pad));
+    *reinterpret_cast<float4*>(xs + rl * kXsStride + lane * 8) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(xs + rl * kXsStride + lane * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    if (row < p.R) {
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(p.xh + (size_t)row * kD + lane * 8) = o;
+      if (lane == 0) p.invn[row] = inv;
+    }
+  }
+  if (__any_sync(0xffffffffu, neg) && lane == 0) *p.negflag = 1;
+  __syncthreads();
+  // ---------------- phase B ----------------
+  const int tg = threadIdx.x & 7, rg = threadIdx.x >> 3;        // token slots tg*TPG.., rows 2rg, 2rg+1
+  const int Pt = p.P1 + p.P2;
+  const int tile_end = min(r0 + 64, p.R);
+  int b = find_segment(p.cu, p.B, r0);
+  for (; b < p.B; ++b) {
+    const int sa = max(__ldg(p.cu + b), r0), sb = min(__ldg(p.cu + b + 1), tile_end);
+    if (__ldg(p.cu + b) >= tile_end) break;
+    if (sa >= sb) continue;
+    __syncthreads();                                             // cs reuse across bags
+    for (int i = threadIdx.x; i < PTPAD * (kD / 4); i += 256) {
+      const int slot = i / (kD / 4), f4 = i % (kD / 4);
+      int src = -1;
+      if (slot < p.P1) src = slot;
+      else if (slot >= p.P1pad && slot - p.P1pad < p.P2) src = p.P1 + slot - p.P1pad;
+      const float4 c = src >= 0 ? __ldg(reinterpret_cast<const float4*>(p.chat + ((size_t)b * Pt + src) * kD) + f4)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(cs + slot * kXsStride + f4 * 4) = c;
+    }
+    __syncthreads();
+    // column sums of the bf16-rounded unit rows of this bag (thread = feature)
+    {
+      float acc = 0.f;
+      for (int r = sa; r < sb; ++r) acc += __bfloat162float(__float2bfloat16_rn(xs[(r - r0) * kXsStride + threadIdx.x]));
+      atomicAdd(p.colsum + (size_t)b * kD + threadIdx.x, acc);
+    }
+    float acc0[TPG], acc1[TPG];
+#pragma unroll
+    for (int j = 0; j < TPG; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+    const float4* x0 = reinterpret_cast<const float4*>(xs + (2 * rg) * kXsStride);
+    const float4* x1 = reinterpret_cast<const float4*>(xs + (2 * rg + 1) * kXsStride);
+    const float4* c4 = reinterpret_cast<const float4*>(cs + (tg * TPG) * kXsStride);
+#pragma unroll 4
+    for (int k4 = 0; k4 < kD / 4; ++k4) {
+      const float4 a = x0[k4], bb = x1[k4];
+#pragma unroll
+      for (int j = 0; j < TPG; ++j) {
+        const float4 c = c4[j * (kXsStride / 4) + k4];
+        acc0[j] = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, acc0[j]))));
+        acc1[j] = fmaf(bb.x, c.x, fmaf(bb.y, c.y, fmaf(bb.z, c.z, fmaf(bb.w, c.w, acc1[j]))));
       }
     }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = r0 + 2 * rg + rr;
+      if (row < sa || row >= sb) continue;
+#pragma unroll
+      for (int j = 0; j < TPG; ++j) {
+        const int slot = tg * TPG + j;
+        const float dot = rr ? acc1[j] : acc0[j];
+        int fix = kNMax;                                          // padding slots have zero tokens: dot == 0
+        if (dot > 0.f) fix = min(kNMax, max(0, __float2int_rn(((float)kCOff - log2f(dot)) * (float)(1 << kLogShift))));
+        // low 5 bits: token index inside its group (column-side operand); the row side masks them off
+        p.lfix[lfix_index(row, slot, PTPAD)] = (float)(fix * 32 + (slot < p.P1pad ? slot : slot - p.P1pad));
+      }
+    }
+  }
+  // rows of the tile past the end of the data keep the sweep's loads finite
+  if (r0 + 64 > p.R) {
+    for (int i = threadIdx.x; i < PTPAD * 64; i += 256) {
+      const int slot = i >> 6, rl = i & 63;
+      if (r0 + rl >= p.R) p.lfix[lfix_index(r0 + rl, slot, PTPAD)] = (float)(kNMax * 32);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// closed-form degrees for non-negative features: d_i = xh_i . S_b - xh_i . xh_i,  e_b = sum_i d_i
+//   (relu is the identity on the Gram matrix when every xh >= 0; the diagonal is excluded, utils.py:194-196)
+// ------------------------------------------------------------------------------------------
+struct DegParams {
+  const bf16* xh;
+  const int* cu;
+  const float* colsum;
+  const int* negflag;
+  float* d;
+  double* e;
+  int R, B;
+};
+__global__ void __launch_bounds__(256) modularity_degrees_closed_kernel(const DegParams p) {
+  if (__ldg(p.negflag)) return;                     // signed features: the Gram sweep computes the degrees
+  __shared__ float s_sum[8];
+  __shared__ int s_bag[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 64 + warp * 8;
+  int cur = -1;
+  float acc = 0.f;
+  float s[8];
+  for (int rr = 0; rr < 8; ++rr) {
+    const int row = r0 + rr;
+    if (row >= p.R) break;
+    int b = cur;
+    if (cur < 0 || row >= __ldg(p.cu + cur + 1)) b = find_segment(p.cu, p.B, row);
+    if (b != cur) {
+      if (cur >= 0 && lane == 0) atomicAdd(p.e + cur, (double)acc);
+      acc = 0.f;
+      cur = b;
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.colsum + (size_t)b * kD + lane * 8));
+      const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.colsum + (size_t)b * kD + lane * 8 + 4));
+      s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+    }
+    const uint4 raw = *reinterpret_cast<const uint4*>(p.xh + (size_t)row * kD + lane * 8);
+    const float v[8] = {bf16lo(raw.x), bf16hi(raw.x), bf16lo(raw.y), bf16hi(raw.y),
+                        bf16lo(raw.z), bf16hi(raw.z), bf16lo(raw.w), bf16hi(raw.w)};
+    float dsum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dsum = fmaf(v[k], s[k] - v[k], dsum);
+    dsum = warp_sum(dsum);
+    if (lane == 0) p.d[row] = dsum;
+    acc += dsum;
+  }
+  if (lane == 0) { s_sum[warp] = acc; s_bag[warp] = cur; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int bag = -1;
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      if (s_bag[w] < 0) continue;
+      if (s_bag[w] != bag) {
+        if (bag >= 0) atomicAdd(p.e + bag, t);
+        bag = s_bag[w];
+        t = 0.0;
+      }
+      t += (double)s_sum[w];
+    }
+    if (bag >= 0) atomicAdd(p.e + bag, t);
   }
 }
 
@@ -133,12 +307,12 @@ __global__ void __launch_bounds__(256) modularity_prep_kernel(const PrepParams p
 // ------------------------------------------------------------------------------------------
 struct GramParams {
   const int* cu;
-  const float* lfix;        // (Rpad, PtPad)
+  const float* lfix;        // tiled, see lfix_index
   float* d;                 // (Rpad) degrees
   double* e;                // (B)
   float* T;                 // (Rpad, PtPad) atomicAdd
   double* s;                // (B, 2 groups): sum_ij (A_ij/e - d_i d_j/e^2) delta_ij
-  const int* nonneg;        // (1) device flag: 1 when every element of h is >= 0 (closed-form degrees were used)
+  const int* negflag;       // (1) device flag: 1 when some element of h is negative (closed-form degrees do not apply)
   int tiles_per_split;      // column tiles per CTA
   float inv_temp;
 };
@@ -148,7 +322,7 @@ constexpr size_t kDegSmem = 1024 + kABytes + kStages * kBBytes + 256;
 __global__ void __launch_bounds__(kThreads, 1)
 modularity_degrees_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                           const GramParams p) {
-  if (p.nonneg && __ldg(p.nonneg)) return;            // degrees came from the closed form (see prep)
+  if (!__ldg(p.negflag)) return;                      // all features >= 0: degrees came from the closed form
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* s_a = smem;
@@ -279,46 +453,28 @@ modularity_degrees_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
 }
 
 // ------------------------------------------------------------------------------------------
-// Pair sweep (traces + T): the dominant kernel of the training step.
-//   CTA = 128 rows x a range of 64-column tiles; 16 warps, thread = (row i, 16 of the 64 columns), 128 registers
-//   per thread (a 17th warp would cap every thread at 96).  There are no dedicated producer / MMA warps: the
-//   pair work of a tile is ~3 us, so lane 0 of warp 0 issues the asynchronous work inline -- at the top of
-//   tile t the TMA loads of B(t+1) and of the L/degree tile t+2, halfway through tile t the tcgen05 MMA of
-//   tile t+1 (128x64x256 into the other TMEM buffer).  Per pair every thread runs
-//     - the (max,x) contraction over tokens as one VIADDMNMX (min form) per (pair, token) on the ALU pipe,
-//       four independent chains per token group;  the row operand carries the float "magic" offset
-//       0x4B000000, so the winning sum IS the bit pattern of the float 2^23 + n and needs no I2F;
-//     - the tanh / gradient tail on packed fp32x2 instructions (FFMA2/FMUL2) over two columns at a time;
+// Pair sweep (the trace and T): the dominant kernel of the training step.
+//   CTA = 128 rows (bag-relative block) x a range of ABSOLUTE 64-column tiles; 16 warps, thread = (row i, 16 of
+//   the 64 columns, four at a time), 128 registers per thread (a 17th warp would cap every thread at 96).
+//   No dedicated producer / MMA warps: the pair work of a tile takes microseconds, so lane 0 of warp 0 drives the
+//   asynchronous machinery from inside the sweep with non-blocking mbarrier probes (four poll points per tile):
+//   bulk copies of the L/degree tiles (4 stages), the TMA load of the B box (1 stage: it is free again as soon
+//   as its MMA retires) and the tcgen05 MMA 128x64x256 into one of four TMEM buffers, up to three tiles ahead.
+//   Per four columns a thread runs
+//     - the (min,+) contraction over tokens: per token pair 2 broadcast 128-bit loads of L (token-major tile),
+//       4 FADD2 (two columns each, row operand broadcast) and 4 FMNMX3 (one per column chain);
+//     - the tanh / gradient tail on packed fp32x2 instructions, two columns per instruction;
 //     - T_i[p*] += t in a thread-private, token-major shared array (bank = thread: conflict free).
 // ------------------------------------------------------------------------------------------
 constexpr int kSwWarps = 16;
-constexpr int kSwEpi = kSwWarps * 32;               // 512 epilogue threads
-constexpr int kSwThreads = kSwEpi;
+constexpr int kSwThreads = kSwWarps * 32;           // 512
 constexpr int kLStages = 4;
-constexpr int kDTile = (kBN + 4) * 4;               // degree tile: 64 floats from a 16-byte aligned start
-
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;"
-      : "=l"(d)
-      : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)), "l"(*reinterpret_cast<uint64_t*>(&c)));
-  return *reinterpret_cast<float2*>(&d);
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
-  return *reinterpret_cast<float2*>(&d);
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
-  return *reinterpret_cast<float2*>(&d);
-}
+constexpr int kTBufs = 4;                           // TMEM accumulator buffers of 64 columns
 
 template <int NQ1, int NQ2>
 constexpr size_t sweep_smem() {
   constexpr int PtPad = 4 * (NQ1 + NQ2);
-  return 1024 + kABytes + kBBytes + (size_t)kLStages * (kBN * PtPad * 4 + kDTile) + (size_t)PtPad * kSwEpi * 4 + 512;
+  return 1024 + kABytes + kBBytes + (size_t)kLStages * (kBN * PtPad * 4 + kBN * 4) + (size_t)PtPad * kSwThreads * 4 + 512;
 }
 
 template <int NQ1, int NQ2>
@@ -328,32 +484,31 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   constexpr int PtPad = 4 * (NQ1 + NQ2);
   constexpr int NG = NQ2 ? 2 : 1;
   constexpr int kLBytes = kBN * PtPad * 4;
-  constexpr int kLStage = kLBytes + kDTile;             // L tile + degree tile
+  constexpr int kLStage = kLBytes + kBN * 4;            // L tile [PtPad][64] + degree tile [64]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* s_a = smem;
   uint8_t* s_b = s_a + kABytes;
   uint8_t* s_l = s_b + kBBytes;
   float* s_T = reinterpret_cast<float*>(s_l + kLStages * kLStage);       // [PtPad][512]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_T + (size_t)PtPad * kSwEpi);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_T + (size_t)PtPad * kSwThreads);
   uint64_t* bfull = bars;                 // TMA -> MMA
   uint64_t* bempty = bars + 1;            // MMA commit -> TMA
-  uint64_t* tfull = bars + 2;             // [2] MMA -> epilogue
-  uint64_t* tempty = bars + 4;            // [2] epilogue -> MMA
-  uint64_t* lfull = bars + 6;             // [kLStages] TMA -> epilogue
-  uint64_t* lempty = lfull + kLStages;    // [kLStages] 16 epilogue warps -> TMA
+  uint64_t* tfull = bars + 2;             // [kTBufs] MMA -> sweep
+  uint64_t* tempty = tfull + kTBufs;      // [kTBufs] 16 warps -> MMA
+  uint64_t* lfull = tempty + kTBufs;      // [kLStages] bulk copy -> sweep
+  uint64_t* lempty = lfull + kLStages;    // [kLStages] 16 warps -> bulk copy
   uint64_t* afull = lempty + kLStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
-  float* s_red = reinterpret_cast<float*>(tmem_slot + 2);                 // [16][4]
+  float* s_red = reinterpret_cast<float*>(tmem_slot + 2);                 // [16][2]
 
   const int b = blockIdx.z;
   const int row_begin = __ldg(p.cu + b), row_end = __ldg(p.cu + b + 1);
-  const int n = row_end - row_begin;
   const int i0 = row_begin + blockIdx.x * kBM;
   if (i0 >= row_end) return;
-  const int ntiles_bag = (n + kBN - 1) / kBN;
-  const int t0 = blockIdx.y * p.tiles_per_split;
-  const int ntiles = max(0, min(ntiles_bag, t0 + p.tiles_per_split) - t0);
+  const int ta0 = row_begin >> 6, ta1 = (row_end + kBN - 1) >> 6;        // absolute column tiles of the bag
+  const int t0 = ta0 + blockIdx.y * p.tiles_per_split;
+  const int ntiles = max(0, min(ta1, t0 + p.tiles_per_split) - t0);
   if (ntiles == 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -361,145 +516,147 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     mbar_init(bfull, 1); mbar_init(bempty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kSwWarps); }
+    for (int i = 0; i < kTBufs; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kSwWarps); }
     for (int i = 0; i < kLStages; ++i) { mbar_init(&lfull[i], 1); mbar_init(&lempty[i], kSwWarps); }
     mbar_init(afull, 1);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  if (warp == 0) tmem_alloc(tmem_slot, kTBufs * kBN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const bool driver = (warp == 0 && lane == 0);       // issues TMA and MMA for the whole CTA
-
-  auto load_b = [&](int it) {                          // B box of tile `it` (single stage: after the MMA of tile it-1)
-    mbar_wait(bempty, (it & 1) ^ 1);
-    mbar_arrive_expect_tx(bfull, kBBytes);
-    const int j0 = row_begin + (t0 + it) * kBN;
-#pragma unroll
-    for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_b + bx * (kBN * 128), &tm_b, bfull, bx * 64, j0);
-  };
-  auto load_l = [&](int it) {                          // L tile + degree tile of tile `it`
-    const int ls = it % kLStages;
-    mbar_wait(&lempty[ls], ((it / kLStages) & 1) ^ 1);
+  // Three single-thread roles, spread over three warps that sit on different scheduler sub-partitions so that
+  // no warp carries all of the issue overhead (one driver warp for everything ran ~35% behind the other 15 and
+  // paced the whole CTA).  The roles only talk through mbarriers:
+  //   role L  (warp 15): bulk copies of the L/degree tiles, gated by lempty
+  //   role B  (warp 14): TMA load of the B box, gated by bempty (= the MMA of the previous tile has retired)
+  //   role M  (warp 13): tcgen05 MMA, gated by bfull and tempty; commits to bempty and tfull
+  const bool role_l = (warp == kSwWarps - 1 && lane == 0);
+  const bool role_b = (warp == kSwWarps - 2 && lane == 0);
+  const bool role_m = (warp == kSwWarps - 3 && lane == 0);
+  int nis = 0;                                         // tiles issued by this thread's role
+  auto issue_l = [&]() {
+    const int ls = nis % kLStages;
     mbar_arrive_expect_tx(&lfull[ls], kLStage);
-    const int j0 = row_begin + (t0 + it) * kBN;
     uint8_t* dst = s_l + (size_t)ls * kLStage;
-    bulk_load(dst, p.lfix + (size_t)j0 * PtPad, kLBytes, &lfull[ls]);
-    bulk_load(dst + kLBytes, p.d + (j0 & ~3), kDTile, &lfull[ls]);        // bulk copies need 16-byte aligned sources
+    const int ta = t0 + nis;
+    bulk_load(dst, p.lfix + (size_t)ta * PtPad * 64, kLBytes, &lfull[ls]);
+    bulk_load(dst + kLBytes, p.d + (size_t)ta * 64, kBN * 4, &lfull[ls]);
+    ++nis;
   };
-  auto issue_mma = [&](int it) {
-    constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
-    const int acc = it & 1;
-    mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
-    mbar_wait(bfull, it & 1);
-    tc_fence_after();
-    const uint32_t sa = smem_u32(s_a), sb = smem_u32(s_b);
+  auto issue_b = [&]() {
+    mbar_arrive_expect_tx(bfull, kBBytes);
 #pragma unroll
-    for (int k = 0; k < kD / 16; ++k) {
-      const uint64_t ad = umma_desc_sw128(sa + (k >> 2) * (kBM * 128) + (k & 3) * 32, 0, 1024);
-      const uint64_t bd = umma_desc_sw128(sb + (k >> 2) * (kBN * 128) + (k & 3) * 32, 0, 1024);
-      umma_f16(tmem_base + acc * kBN, ad, bd, idesc, k != 0);
-    }
-    umma_commit(bempty);
-    umma_commit(&tfull[acc]);
+    for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_b + bx * (kBN * 128), &tm_b, bfull, bx * 64, (t0 + nis) * kBN);
+    ++nis;
   };
-  if (driver) {
+  auto issue_mma = [&]() {
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
+    tc_fence_after();
+    const uint64_t ad0 = umma_desc_sw128(smem_u32(s_a), 0, 1024), bd0 = umma_desc_sw128(smem_u32(s_b), 0, 1024);
+    const uint32_t tacc = tmem_base + (nis % kTBufs) * kBN;
+#pragma unroll
+    for (int k = 0; k < kD / 16; ++k)      // descriptor start addresses advance in 16-byte units
+      umma_f16(tacc, ad0 + (uint64_t)(((k >> 2) * (kBM * 128) + (k & 3) * 32) >> 4),
+               bd0 + (uint64_t)(((k >> 2) * (kBN * 128) + (k & 3) * 32) >> 4), idesc, k != 0);
+    umma_commit(bempty);
+    umma_commit(&tfull[nis % kTBufs]);
+    ++nis;
+  };
+  // non-blocking: issue the next item of this thread's role if its gate is open
+  auto poll = [&]() {
+    if (nis >= ntiles) return;
+    if (role_l) { if (mbar_test(&lempty[nis % kLStages], ((nis / kLStages) & 1) ^ 1)) issue_l(); }
+    else if (role_b) { if (mbar_test(bempty, (nis & 1) ^ 1)) issue_b(); }
+    else if (mbar_test(bfull, nis & 1) && mbar_test(&tempty[nis % kTBufs], ((nis / kTBufs) & 1) ^ 1)) issue_mma();
+  };
+  // blocking: the item tile `it` needs has been issued (its gates only depend on strictly older tiles)
+  auto ensure = [&](int it) {
+    while (nis <= it) {
+      if (role_l) { mbar_wait(&lempty[nis % kLStages], ((nis / kLStages) & 1) ^ 1); issue_l(); }
+      else if (role_b) { mbar_wait(bempty, (nis & 1) ^ 1); issue_b(); }
+      else { mbar_wait(bfull, nis & 1); mbar_wait(&tempty[nis % kTBufs], ((nis / kTBufs) & 1) ^ 1); issue_mma(); }
+    }
+  };
+  const bool driver = role_l || role_b || role_m;
+  if (role_m) {
     mbar_arrive_expect_tx(afull, kABytes);
 #pragma unroll
     for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_a + bx * (kBM * 128), &tm_a, afull, bx * 64, i0);
-    load_b(0);
-    load_l(0);
-    if (ntiles > 1) load_l(1);
     mbar_wait(afull, 0);
-    issue_mma(0);
   }
-  {
-    // ------------------------------ epilogue: thread = (row i, 16 of the 64 columns) ------------------
-    const int q = warp & 3, hc = warp >> 2;
-    const int tid = threadIdx.x;                       // = hc*128 + row in block
-    const int i = i0 + q * 32 + lane;
-    const bool row_ok = i < row_end;
-    float* myT = s_T + tid;                            // element p at myT[p * 512]
-    float2 Li[PtPad / 2];                              // row operand, token pairs: 2^23 + (N_i << 5)
-#pragma unroll
-    for (int k = 0; k < PtPad; k += 2) {
-      const float2 w = row_ok ? __ldg(reinterpret_cast<const float2*>(p.lfix + (size_t)i * PtPad + k))
-                              : make_float2((float)(kNMax << 5), (float)(kNMax << 5));
-      Li[k >> 1] = make_float2((float)((int)w.x & ~31) + 8388608.f, (float)((int)w.y & ~31) + 8388608.f);
-      myT[k * kSwEpi] = 0.f;
-      myT[(k + 1) * kSwEpi] = 0.f;
-    }
-    const float di = row_ok ? __ldg(p.d + i) : 0.f;
-    const double e = p.e[b];
-    const float k1 = (float)(1.0 / e), k2 = (float)(1.0 / (e * e));
-    const float gs4 = -800.f * p.inv_temp;                                 // 4 * 2 * (-100) / temp
-    const float2 c0 = make_float2(gs4 * k1, gs4 * k1);
-    const float2 nci = make_float2(-gs4 * k2 * di, -gs4 * k2 * di);
-    const float nx2 = -2.f * 1.4426950408889634f * p.inv_temp;             // tanh(u/temp) via exp2(-2 u log2e / temp)
-    const float2 nx2s = make_float2(nx2, nx2);
-    const float2 kscale = make_float2(-1.f / (float)(1 << (kLogShift + 5)), -1.f / (float)(1 << (kLogShift + 5)));
-    const float2 koff = make_float2(kArgOff, kArgOff);
-    const float2 one2 = make_float2(1.f, 1.f), neg2 = make_float2(-1.f, -1.f);
-    float2 sg[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 
-    for (int it = 0; it < ntiles; ++it) {
-      const int acc = it & 1, ls = it % kLStages;
-      if (driver) {
-        if (it + 1 < ntiles) load_b(it + 1);
-        if (it + 2 < ntiles) load_l(it + 2);
+  const int q = warp & 3, hc = warp >> 2;
+  const int tid = threadIdx.x;                         // = hc*128 + row in block
+  const int i = i0 + q * 32 + lane;
+  const bool row_ok = i < row_end;
+  float* myT = s_T + tid;                              // element p at myT[p * 512]
+  float Li[PtPad];                                     // row operand: 2^23 + (N_i << 5)
+#pragma unroll
+  for (int k = 0; k < PtPad; ++k) {
+    const float w = row_ok ? __ldg(p.lfix + lfix_index(i, k, PtPad)) : (float)(kNMax << 5);
+    Li[k] = (float)((int)w & ~31) + 8388608.f;
+    myT[k * kSwThreads] = 0.f;
+  }
+  const float di = row_ok ? __ldg(p.d + i) : 0.f;
+  const double e = p.e[b];
+  const float k1 = (float)(1.0 / e), k2 = (float)(1.0 / (e * e));
+  const float gs4 = -800.f * p.inv_temp;                                 // 4 * 2 * (-100) / temp
+  const float2 c0 = make_float2(gs4 * k1, gs4 * k1);
+  const float2 nci = make_float2(-gs4 * k2 * di, -gs4 * k2 * di);
+  const float nx2 = -2.f * 1.4426950408889634f * p.inv_temp;             // tanh(u/temp) via exp2(-2 u log2e / temp)
+  const float2 nx2s = make_float2(nx2, nx2);
+  const float2 kscale = make_float2(-1.f / (float)(1 << (kLogShift + 5)), -1.f / (float)(1 << (kLogShift + 5)));
+  const float2 koff = make_float2(kArgOff, kArgOff);
+  const float2 one2 = make_float2(1.f, 1.f), neg2 = make_float2(-1.f, -1.f);
+  float2 sg[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+
+  for (int it = 0; it < ntiles; ++it) {
+    const int tb = it % kTBufs, ls = it % kLStages;
+    if (driver) { ensure(it); poll(); }
+    __syncwarp();
+    mbar_wait(&tfull[tb], (it / kTBufs) & 1);
+    tc_fence_after();
+    mbar_wait(&lfull[ls], (it / kLStages) & 1);
+    const uint8_t* st = s_l + (size_t)ls * kLStage;
+    const float4* sL = reinterpret_cast<const float4*>(st) + hc * 4;               // [token][16 float4]: + token*16 + g
+    const float4* sd = reinterpret_cast<const float4*>(st + kLBytes) + hc * 4;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + tb * kBN + hc * 16;
+    const int jt0 = (t0 + it) * kBN;
+    const bool interior = (i0 + kBM <= row_end) && (jt0 >= row_begin) && (jt0 + kBN <= row_end) &&
+                          (jt0 >= i0 + kBM || jt0 + kBN <= i0);
+
+    auto group4 = [&](int g, auto interior_tag) {
+      constexpr bool INTERIOR = decltype(interior_tag)::value;
+      uint32_t v[4];
+      tmem_ld4(taddr + g * 4, v);                       // Gram values of the 4 columns (consumed after the contraction)
+      float m[4][2];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { m[c][0] = 3e38f; m[c][1] = 3e38f; }
+#pragma unroll
+      for (int pp = 0; pp < PtPad / 2; ++pp) {
+        constexpr int dummy = 0; (void)dummy;
+        const int grp = (2 * pp >= 4 * NQ1) ? 1 : 0;
+        const float4 w0 = sL[(2 * pp) * 16 + g];
+        const float4 w1 = sL[(2 * pp + 1) * 16 + g];
+        const float2 la = make_float2(Li[2 * pp], Li[2 * pp]), lb = make_float2(Li[2 * pp + 1], Li[2 * pp + 1]);
+        const float2 a01 = add2(make_float2(w0.x, w0.y), la), a23 = add2(make_float2(w0.z, w0.w), la);
+        const float2 b01 = add2(make_float2(w1.x, w1.y), lb), b23 = add2(make_float2(w1.z, w1.w), lb);
+        m[0][grp] = fminf(fminf(a01.x, b01.x), m[0][grp]);
+        m[1][grp] = fminf(fminf(a01.y, b01.y), m[1][grp]);
+        m[2][grp] = fminf(fminf(a23.x, b23.x), m[2][grp]);
+        m[3][grp] = fminf(fminf(a23.y, b23.y), m[3][grp]);
       }
-      __syncwarp();
-      mbar_wait(&tfull[acc], (it >> 1) & 1);
-      tc_fence_after();
-      uint32_t v[8];                                     // columns 0-7 now, 8-15 halfway through the tile
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kBN + hc * 16;
-      tmem_ld8(taddr, v);
       tmem_ld_wait();
-      mbar_wait(&lfull[ls], (it / kLStages) & 1);
-      const uint8_t* st = s_l + (size_t)ls * kLStage;
-      const float4* sL = reinterpret_cast<const float4*>(st) + (size_t)hc * 16 * (PtPad / 4);
-      const int jt0 = row_begin + (t0 + it) * kBN;
-      const float* sd = reinterpret_cast<const float*>(st + kLBytes) + (jt0 & 3) + hc * 16;
-      const int jbase = jt0 + hc * 16;
-      const bool interior = (i0 + kBM <= row_end) && (jt0 + kBN <= row_end) && (jt0 >= i0 + kBM || jt0 + kBN <= i0);
-
-      // (min,+) contraction over tokens: one packed FADD2 (FMA pipe) per token PAIR, one 3-input FMNMX3
-      // (ALU pipe) folding both sums into one of four independent chains per token group
-      auto chains = [&](int jj, int (&m)[2][2]) {
+      const float4 dj4 = sd[g];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const float4* lj = sL + (jj + c) * (PtPad / 4);
-          float ch[4] = {3e38f, 3e38f, 3e38f, 3e38f};
-#pragma unroll
-          for (int qd = 0; qd < NQ1; ++qd) {
-            const float4 w = lj[qd];
-            const float2 sa = add2(Li[2 * qd], make_float2(w.x, w.y));
-            const float2 sb = add2(Li[2 * qd + 1], make_float2(w.z, w.w));
-            ch[(2 * qd) & 3] = fminf(fminf(sa.x, sa.y), ch[(2 * qd) & 3]);
-            ch[(2 * qd + 1) & 3] = fminf(fminf(sb.x, sb.y), ch[(2 * qd + 1) & 3]);
-          }
-          m[c][0] = __float_as_int(fminf(fminf(ch[0], ch[1]), fminf(ch[2], ch[3])));
-          float cg[4] = {3e38f, 3e38f, 3e38f, 3e38f};
-#pragma unroll
-          for (int qd = 0; qd < NQ2; ++qd) {
-            const float4 w = lj[NQ1 + qd];
-            const float2 sa = add2(Li[2 * (NQ1 + qd)], make_float2(w.x, w.y));
-            const float2 sb = add2(Li[2 * (NQ1 + qd) + 1], make_float2(w.z, w.w));
-            cg[(2 * qd) & 3] = fminf(fminf(sa.x, sa.y), cg[(2 * qd) & 3]);
-            cg[(2 * qd + 1) & 3] = fminf(fminf(sb.x, sb.y), cg[(2 * qd + 1) & 3]);
-          }
-          m[c][1] = NQ2 ? __float_as_int(fminf(fminf(cg[0], cg[1]), fminf(cg[2], cg[3]))) : 0;
-        }
-      };
-      auto tail = [&](int jj, const int (&m)[2][2], auto interior_tag) {
-        constexpr bool INTERIOR = decltype(interior_tag)::value;
-        float2 a2 = make_float2(fmaxf(__uint_as_float(v[jj & 7]), 0.f), fmaxf(__uint_as_float(v[(jj & 7) + 1]), 0.f));
-        float2 dj2 = make_float2(sd[jj], sd[jj + 1]);
+      for (int h2 = 0; h2 < 2; ++h2) {                  // column pairs (0,1) and (2,3)
+        float2 a2 = make_float2(fmaxf(__uint_as_float(v[2 * h2]), 0.f), fmaxf(__uint_as_float(v[2 * h2 + 1]), 0.f));
+        float2 dj2 = h2 ? make_float2(dj4.z, dj4.w) : make_float2(dj4.x, dj4.y);
         if (!INTERIOR) {
-          const int j = jbase + jj;
-          const bool ok0 = row_ok && j < row_end, ok1 = row_ok && j + 1 < row_end;
+          const int j = jt0 + hc * 16 + g * 4 + 2 * h2;
+          const bool ok0 = row_ok && j >= row_begin && j < row_end, ok1 = row_ok && j + 1 >= row_begin && j + 1 < row_end;
           a2.x = (ok0 && j != i) ? a2.x : 0.f;
           a2.y = (ok1 && j + 1 != i) ? a2.y : 0.f;
           dj2.x = ok0 ? dj2.x : 0.f;
@@ -508,11 +665,11 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
         const float2 gw = fma2(a2, c0, mul2(dj2, nci));                 // 4*2*(-100)/temp * (A/e - d_i d_j/e^2); 0 when masked
 #pragma unroll
         for (int grp = 0; grp < NG; ++grp) {
-          const int m0 = m[0][grp], m1 = m[1][grp];
+          const int m0 = __float_as_int(m[2 * h2][grp]), m1 = __float_as_int(m[2 * h2 + 1][grp]);
           const int pl0 = m0 & 31, pl1 = m1 & 31;
           const float2 F = make_float2(__int_as_float(m0 & ~31), __int_as_float(m1 & ~31));
           const float2 arg = fma2(F, kscale, koff);                     // log2(C_i C_j) of the winning token
-          float2 u = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
+          const float2 u = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
           const float2 x = mul2(u, nx2s);
           const float2 e2 = make_float2(ex2_approx(x.x), ex2_approx(x.y));   // exp(-2u/temp)
           const float2 den = add2(e2, one2);
@@ -521,66 +678,62 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
           const float2 delta = fma2(t1, neg2, r);                       // tanh(u/temp) = (1-e2)/(1+e2)
           sg[grp] = fma2(gw, delta, sg[grp]);                           // sum of gs4 * (A/e - d_i d_j/e^2) * delta
           const float2 t = mul2(mul2(gw, t1), mul2(r, u));              // 2 g (1-delta^2)/temp * u, 1-delta^2 = 4 e2 r^2
-          float* T0 = myT + (size_t)(pl0 + (grp ? 4 * NQ1 : 0)) * kSwEpi;
+          float* T0 = myT + (size_t)(pl0 + (grp ? 4 * NQ1 : 0)) * kSwThreads;
           *T0 += t.x;
-          float* T1 = myT + (size_t)(pl1 + (grp ? 4 * NQ1 : 0)) * kSwEpi;
+          float* T1 = myT + (size_t)(pl1 + (grp ? 4 * NQ1 : 0)) * kSwThreads;
           *T1 += t.y;
         }
-      };
-      auto sweep = [&](auto interior_tag) {
-#pragma unroll
-        for (int jj = 0; jj < 16; jj += 2) {
-          int m[2][2];
-          chains(jj, m);
-          tail(jj, m, interior_tag);
-          if (jj == 6) {                                 // second half of the accumulator row, then release the TMEM buffer
-            tmem_ld8(taddr + 8, v);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (driver && it + 1 < ntiles) issue_mma(it + 1);
-            __syncwarp();
-          }
-        }
-      };
-      if (interior) sweep(std::true_type{}); else sweep(std::false_type{});
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&lempty[ls]);
-    }
-    // ---------------- flush ----------------
-    {
-      const float inv_gs4 = 1.f / gs4;
-#pragma unroll
-      for (int grp = 0; grp < 2; ++grp) {
-        const float a1 = warp_sum((sg[grp].x + sg[grp].y) * inv_gs4);   // = sum A delta / e - sum d_i d_j delta / e^2
-        if (lane == 0) s_red[warp * 2 + grp] = a1;
       }
+    };
+    auto tile = [&](auto interior_tag) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        group4(g, interior_tag);
+        if (g == 3) {                                    // the accumulator buffer has been read completely
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[tb]);
+        }
+        if (driver) poll();
+        __syncwarp();
+      }
+    };
+    if (interior) tile(std::true_type{}); else tile(std::false_type{});
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&lempty[ls]);
+  }
+  // ---------------- flush ----------------
+  {
+    const float inv_gs4 = 1.f / gs4;
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp) {
+      const float a1 = warp_sum((sg[grp].x + sg[grp].y) * inv_gs4);   // = sum A delta / e - sum d_i d_j delta / e^2
+      if (lane == 0) s_red[warp * 2 + grp] = a1;
     }
-    asm volatile("bar.sync 1, %0;" ::"r"(kSwEpi) : "memory");
-    if (tid < 2) {
-      double t = 0.0;
-      for (int w = 0; w < kSwWarps; ++w) t += (double)s_red[w * 2 + tid];
-      atomicAdd(p.s + (size_t)b * 2 + tid, t);
-    }
-    // the four column-quarter threads of a row are combined before one RED per (row, token)
-    for (int idx = tid; idx < kBM * PtPad; idx += kSwEpi) {
-      const int r = idx & (kBM - 1), k = idx >> 7;
-      const float* src = s_T + (size_t)k * kSwEpi + r;
-      const float t = (src[0] + src[kBM]) + (src[2 * kBM] + src[3 * kBM]);
-      if (t != 0.f && i0 + r < row_end) atomicAdd(p.T + (size_t)(i0 + r) * PtPad + k, t);
-    }
+  }
+  __syncthreads();
+  if (tid < 2) {
+    double t = 0.0;
+    for (int w = 0; w < kSwWarps; ++w) t += (double)s_red[w * 2 + tid];
+    atomicAdd(p.s + (size_t)b * 2 + tid, t);
+  }
+  // the four column-quarter threads of a row are combined before one RED per (row, token)
+  for (int idx = tid; idx < kBM * PtPad; idx += kSwThreads) {
+    const int r = idx & (kBM - 1), k = idx >> 7;
+    const float* src = s_T + (size_t)k * kSwThreads + r;
+    const float t = (src[0] + src[kBM]) + (src[2 * kBM] + src[3 * kBM]);
+    if (t != 0.f && i0 + r < row_end) atomicAdd(p.T + (size_t)(i0 + r) * PtPad + k, t);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_base, kTBufs * kBN);
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// finish: dC = T / C (C = exp2(L)), dchat_p = sum_i dC_ip xh_i ; loss per group
+// finish: dC = T / C (C = exp2(kCOff - N/2^kLogShift)), dchat_p = sum_i dC_ip xh_i ; loss per group
 //   grid (row chunks, B), 256 threads = features; dchat accumulated with atomicAdd
 // ------------------------------------------------------------------------------------------
 struct FinishParams {
@@ -590,15 +743,14 @@ struct FinishParams {
   const float* T;
   const int* cu;
   const double* s;
-  const double* e;
   float* dchat;       // (B, Pt, 256), zeroed by the launcher
   float* loss;        // (B, 2)
-  int P1, P2, P1pad, PtPad, rows_per_cta;
+  int P1, P2, P1pad, rows_per_cta;
 };
 
 template <int PTPAD>
 __global__ void __launch_bounds__(256) modularity_finish_kernel(const FinishParams p) {
-  __shared__ float s_dc[32][PTPAD];
+  __shared__ __align__(16) float s_dc[32][PTPAD];
   const int b = blockIdx.y, f = threadIdx.x;
   const int row_begin = __ldg(p.cu + b), row_end = __ldg(p.cu + b + 1);
   const int Pt = p.P1 + p.P2;
@@ -618,10 +770,9 @@ __global__ void __launch_bounds__(256) modularity_finish_kernel(const FinishPara
       const int r = idx / PTPAD, k = idx % PTPAD;
       float v = 0.f;
       if (r < nr) {
-        const size_t o = (size_t)(rb + r) * PTPAD + k;
-        const float t = p.T[o];
+        const float t = p.T[(size_t)(rb + r) * PTPAD + k];
         if (t != 0.f) {
-          const int nfix = (int)p.lfix[o] >> 5;
+          const int nfix = (int)p.lfix[lfix_index(rb + r, k, PTPAD)] >> 5;
           const float c = ex2_approx((float)kCOff - (float)nfix * (1.f / (float)(1 << kLogShift)));
           v = nfix < kNMax ? t / c : 0.f;              // relu gate: C == 0 never wins the max with u > 0
         }
@@ -631,8 +782,15 @@ __global__ void __launch_bounds__(256) modularity_finish_kernel(const FinishPara
     __syncthreads();
     for (int r = 0; r < nr; ++r) {
       const float xv = __bfloat162float(p.h[(size_t)(rb + r) * kD + f]) * __ldg(p.invn + rb + r);
+      const float4* dc4 = reinterpret_cast<const float4*>(&s_dc[r][0]);
 #pragma unroll
-      for (int k = 0; k < PTPAD; ++k) acc[k] += s_dc[r][k] * xv;
+      for (int k4 = 0; k4 < PTPAD / 4; ++k4) {
+        const float4 dcv = dc4[k4];
+        acc[4 * k4 + 0] = fmaf(dcv.x, xv, acc[4 * k4 + 0]);
+        acc[4 * k4 + 1] = fmaf(dcv.y, xv, acc[4 * k4 + 1]);
+        acc[4 * k4 + 2] = fmaf(dcv.z, xv, acc[4 * k4 + 2]);
+        acc[4 * k4 + 3] = fmaf(dcv.w, xv, acc[4 * k4 + 3]);
+      }
     }
   }
 #pragma unroll
@@ -644,9 +802,8 @@ __global__ void __launch_bounds__(256) modularity_finish_kernel(const FinishPara
   }
 }
 
-int pad4(int v) { return (v + 3) & ~3; }
 int quads1(int P1) { return P1 <= 8 ? 2 : (P1 <= 16 ? 4 : 8); }
-int quads2(int P2) { return P2 == 0 ? 0 : (P2 <= 8 ? 2 : (P2 <= 16 ? 4 : 8)); }
+int quads2(int P2) { return P2 == 0 ? 0 : 2; }
 
 int run_degrees(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p, dim3 grid, cudaStream_t st) {
   static bool done = false;
@@ -654,7 +811,7 @@ int run_degrees(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& 
     IMP_CUDA(cudaFuncSetAttribute(modularity_degrees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDegSmem));
     done = true;
   }
-  IMP_LAUNCH("modularity_gram_degrees", st, modularity_degrees_kernel<<<grid, kThreads, kDegSmem, st>>>(ta, tb, p));
+  IMP_LAUNCH("modularity_degrees_gram", st, modularity_degrees_kernel<<<grid, kThreads, kDegSmem, st>>>(ta, tb, p));
   return IMP_OK;
 }
 
@@ -671,24 +828,39 @@ int run_sweep(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p,
   return IMP_OK;
 }
 
+template <int PTPAD>
+int run_prep(const PrepParams& pp, cudaStream_t st) {
+  constexpr size_t smem = prep_smem<PTPAD>();
+  static bool done = false;
+  if (!done) {
+    IMP_CUDA(cudaFuncSetAttribute(modularity_prep_kernel<PTPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done = true;
+  }
+  IMP_LAUNCH("modularity_prep", st, modularity_prep_kernel<PTPAD><<<(pp.R + 63) / 64, 256, smem, st>>>(pp));
+  return IMP_OK;
+}
+
 struct Carve {
-  bf16* xh; float* invn; float* lfix; float* d; float* T; double* e; double* s;
+  bf16* xh; float* invn; float* lfix; float* d; float* T; double* e; double* s; float* colsum; int* negflag;
   size_t zero_off, zero_bytes, total;
 };
 Carve carve(void* ws, int total_rows, int B, int PtPad) {
-  const size_t rpad = (size_t)total_rows + kBM;
+  const size_t rpad = (size_t)total_rows + kBM + kBN;
+  const size_t ntile = (rpad + 63) / 64;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   uint8_t* base = reinterpret_cast<uint8_t*>(ws);
   size_t off = 0;
   Carve c;
   c.xh = reinterpret_cast<bf16*>(base + off); off += up(rpad * kD * 2);
   c.invn = reinterpret_cast<float*>(base + off); off += up(rpad * 4);
-  c.lfix = reinterpret_cast<float*>(base + off); off += up(rpad * PtPad * 4);
+  c.lfix = reinterpret_cast<float*>(base + off); off += up(ntile * PtPad * 64 * 4);
   c.zero_off = off;
   c.d = reinterpret_cast<float*>(base + off); off += up(rpad * 4);
   c.T = reinterpret_cast<float*>(base + off); off += up(rpad * PtPad * 4);
   c.e = reinterpret_cast<double*>(base + off); off += up((size_t)B * 8);
   c.s = reinterpret_cast<double*>(base + off); off += up((size_t)B * 2 * 8);
+  c.colsum = reinterpret_cast<float*>(base + off); off += up((size_t)B * kD * 4);
+  c.negflag = reinterpret_cast<int*>(base + off); off += up(4);
   c.zero_bytes = off - c.zero_off;
   c.total = off;
   return c;
@@ -704,57 +876,59 @@ size_t modularity_workspace_bytes(int total_rows, int B, int P1, int P2) {
 int launch_modularity(const bf16* h, int total_rows, const int* cu, int B, int max_len, const float* chat, int P1, int P2,
                       float temp, void* workspace, float* loss, float* dchat, cudaStream_t st) {
   if (B <= 0) return IMP_OK;
-  if (P1 < 1 || P1 > 32 || P2 < 0 || P2 > 32) IMP_FAIL(IMP_ERR_ARG, "modularity: token groups (%d,%d) must be in [1,32] and [0,32]", P1, P2);
+  if (P1 < 1 || P1 > 32 || P2 < 0 || P2 > 8) IMP_FAIL(IMP_ERR_ARG, "modularity: token groups (%d,%d) must be in [1,32] and [0,8]", P1, P2);
   if (total_rows <= 0 || max_len <= 0) IMP_FAIL(IMP_ERR_ARG, "modularity: empty input");
   if (!(temp > 0.f)) IMP_FAIL(IMP_ERR_ARG, "modularity: temp must be positive");
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) IMP_FAIL(IMP_ERR_ARG, "modularity: workspace must be 256-byte aligned");
   const int nq1 = quads1(P1), nq2 = quads2(P2);
   const int P1pad = 4 * nq1, PtPad = 4 * (nq1 + nq2), Pt = P1 + P2;
   Carve c = carve(workspace, total_rows, B, PtPad);
-  // padding rows of xh / lfix are read by the tile loads of the last row block: keep them finite
-  IMP_CUDA(cudaMemsetAsync(c.xh + (size_t)total_rows * kD, 0, (size_t)kBM * kD * 2, st));
-  IMP_CUDA(cudaMemsetAsync(c.lfix + (size_t)total_rows * PtPad, 0, (size_t)kBM * PtPad * 4, st));
+  // padding rows of xh are read by the tile loads of the last row block / column tile: keep them finite
+  IMP_CUDA(cudaMemsetAsync(c.xh + (size_t)total_rows * kD, 0, (size_t)(kBM + kBN) * kD * 2, st));
   IMP_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(workspace) + c.zero_off, 0, c.zero_bytes, st));
   IMP_CUDA(cudaMemsetAsync(dchat, 0, (size_t)B * Pt * kD * 4, st));
 
   PrepParams pp;
-  pp.h = h; pp.cu = cu; pp.chat = chat; pp.xh = c.xh; pp.invn = c.invn; pp.lfix = c.lfix;
-  pp.B = B; pp.P1 = P1; pp.P2 = P2; pp.P1pad = P1pad; pp.PtPad = PtPad;
-  const size_t prep_smem = (size_t)PtPad * kD * 4;
-  static bool prep_attr = false;
-  if (!prep_attr) {
-    IMP_CUDA(cudaFuncSetAttribute(modularity_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * kD * 4));
-    prep_attr = true;
+  pp.h = h; pp.cu = cu; pp.chat = chat; pp.xh = c.xh; pp.invn = c.invn; pp.lfix = c.lfix; pp.colsum = c.colsum;
+  pp.negflag = c.negflag; pp.R = total_rows; pp.B = B; pp.P1 = P1; pp.P2 = P2; pp.P1pad = P1pad;
+  int rc;
+  switch (PtPad) {
+    case 8: rc = run_prep<8>(pp, st); break;
+    case 16: rc = run_prep<16>(pp, st); break;
+    case 24: rc = run_prep<24>(pp, st); break;
+    case 32: rc = run_prep<32>(pp, st); break;
+    case 40: rc = run_prep<40>(pp, st); break;
+    default: IMP_FAIL(IMP_ERR_ARG, "modularity: unsupported padded token count %d", PtPad);
   }
-  const int prep_chunks = std::max(1, std::min((max_len + 7) / 8, (4 * imp_num_sms() + B - 1) / B));
-  IMP_LAUNCH("modularity_prep", st, modularity_prep_kernel<<<dim3(prep_chunks, B), 256, prep_smem, st>>>(pp));
+  if (rc) return rc;
+
+  DegParams dp;
+  dp.xh = c.xh; dp.cu = cu; dp.colsum = c.colsum; dp.negflag = c.negflag; dp.d = c.d; dp.e = c.e; dp.R = total_rows; dp.B = B;
+  IMP_LAUNCH("modularity_degrees_closed", st, modularity_degrees_closed_kernel<<<(total_rows + 63) / 64, 256, 0, st>>>(dp));
 
   CUtensorMap ta, tb;
-  int rc;
-  const uint64_t rpad = (uint64_t)total_rows + kBM;
+  const uint64_t rpad = (uint64_t)total_rows + kBM + kBN;
   if ((rc = imp_make_tmap_2d(&ta, c.xh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, rpad, kD * 2, 64, kBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = imp_make_tmap_2d(&tb, c.xh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, rpad, kD * 2, 64, kBN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   GramParams gp;
-  gp.cu = cu; gp.lfix = c.lfix; gp.d = c.d; gp.e = c.e; gp.T = c.T; gp.s = c.s; gp.inv_temp = 1.f / temp;
+  gp.cu = cu; gp.lfix = c.lfix; gp.d = c.d; gp.e = c.e; gp.T = c.T; gp.s = c.s; gp.negflag = c.negflag; gp.inv_temp = 1.f / temp;
   const int row_blocks = (max_len + kBM - 1) / kBM;
-  const int col_tiles = (max_len + kBN - 1) / kBN;
+  const int col_tiles = (max_len + kBN - 1) / kBN + 1;        // absolute tiles: a bag may straddle one more
   // enough CTAs for >= 2 waves; at least 16 column tiles per CTA to amortise the A block load
   int nsplit = std::max(1, std::min((2 * imp_num_sms() + row_blocks * B - 1) / (row_blocks * B), std::max(1, col_tiles / 16)));
   gp.tiles_per_split = (col_tiles + nsplit - 1) / nsplit;
   nsplit = (col_tiles + gp.tiles_per_split - 1) / gp.tiles_per_split;
   const dim3 grid(row_blocks, nsplit, B);
-  gp.nonneg = nullptr;
-  if ((rc = run_degrees(ta, tb, gp, grid, st))) return rc;
+  if ((rc = run_degrees(ta, tb, gp, grid, st))) return rc;     // exits at once unless some feature is negative
 #define IMP_SWEEP(a, b2) rc = run_sweep<a, b2>(ta, tb, gp, grid, st)
   if (nq2 == 0) { if (nq1 == 2) IMP_SWEEP(2, 0); else if (nq1 == 4) IMP_SWEEP(4, 0); else IMP_SWEEP(8, 0); }
-  else if (nq2 == 2) { if (nq1 == 2) IMP_SWEEP(2, 2); else if (nq1 == 4) IMP_SWEEP(4, 2); else IMP_SWEEP(8, 2); }
-  else IMP_FAIL(IMP_ERR_ARG, "modularity: second token group supports at most 8 tokens (got %d)", P2);
+  else { if (nq1 == 2) IMP_SWEEP(2, 2); else if (nq1 == 4) IMP_SWEEP(4, 2); else IMP_SWEEP(8, 2); }
 #undef IMP_SWEEP
   if (rc) return rc;
 
   FinishParams fp;
-  fp.h = h; fp.invn = c.invn; fp.lfix = c.lfix; fp.T = c.T; fp.cu = cu; fp.s = c.s; fp.e = c.e;
-  fp.dchat = dchat; fp.loss = loss; fp.P1 = P1; fp.P2 = P2; fp.P1pad = P1pad; fp.PtPad = PtPad;
+  fp.h = h; fp.invn = c.invn; fp.lfix = c.lfix; fp.T = c.T; fp.cu = cu; fp.s = c.s;
+  fp.dchat = dchat; fp.loss = loss; fp.P1 = P1; fp.P2 = P2; fp.P1pad = P1pad;
   const int fin_chunks = std::max(1, std::min((max_len + 255) / 256, (4 * imp_num_sms() + B - 1) / B));
   fp.rows_per_cta = ((max_len + fin_chunks - 1) / fin_chunks + 31) & ~31;
   const dim3 fgrid((max_len + fp.rows_per_cta - 1) / fp.rows_per_cta, B);

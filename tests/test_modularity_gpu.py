@@ -1,12 +1,17 @@
 """A4-A6 modularity kernels vs the CPU oracle (chunked fp64 restatement of ops/utils.py:178-228)
 on the same bf16-rounded patch tokens.  Tolerance 1e-3 relative (north_star) on the loss and,
-as relative Frobenius error, on the gradient wrt the tokens."""
+as relative Frobenius error, 2e-3 on the gradient wrt the tokens.
+
+The loss is -100 (S1 - S2) with S1 = sum A delta / e and S2 = sum d_i d_j delta / e^2 both in [0,1] and nearly
+equal on small graphs (|loss| ~ 1e-2 against a scale of 100): the absolute term ABS_TOL = 5e-5 is 5e-7 of that
+scale and covers the cancellation; it is far below 1e-3 of the training loss the term is added to."""
 import pytest
 import torch
 
 from util_hotpath import rel
 
 pytestmark = pytest.mark.gpu
+ABS_TOL = 5e-5
 
 
 def _inputs(n, p, q, seed):
@@ -31,11 +36,11 @@ def test_modularity_vs_oracle(n, p, q):
     (loss[0, 0] * 1.0 + loss[0, 1] * 2.0).backward()
     torch.cuda.synchronize()
     ref1, dref1 = O.modularity(c1, h.float(), chunk=256)
-    assert abs(loss[0, 0].item() - ref1.item()) <= 1e-3 * abs(ref1.item()) + 1e-5, (loss[0, 0].item(), ref1.item())
+    assert abs(loss[0, 0].item() - ref1.item()) <= 1e-3 * abs(ref1.item()) + ABS_TOL, (loss[0, 0].item(), ref1.item())
     assert rel(c1d.grad[0], dref1) < 2e-3, rel(c1d.grad[0], dref1)
     if q:
         ref2, dref2 = O.modularity(c2, h.float(), chunk=256)
-        assert abs(loss[0, 1].item() - ref2.item()) <= 1e-3 * abs(ref2.item()) + 1e-5
+        assert abs(loss[0, 1].item() - ref2.item()) <= 1e-3 * abs(ref2.item()) + ABS_TOL
         assert rel(c2d.grad[0], 2.0 * dref2) < 2e-3, rel(c2d.grad[0], 2.0 * dref2)
 
 
@@ -54,27 +59,21 @@ def test_modularity_batched_varlen_matches_single():
         assert abs(batched[i, 0].item() - single.item()) <= 1e-4 * abs(single.item()) + 1e-6
 
 
-def test_symmetric_pair_sweep_matches_full_sweep():
-    """The upper-triangular sweep (IMP_MODULARITY_SYMMETRIC=1) and the default full sweep are two kernels
-    for the same sums: run both in fresh processes (the switch is read once) and compare."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = (
-        "import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests');"
-        "import imp_b200; from imp_b200 import modularity as M; from test_modularity_gpu import _inputs;"
-        "h, c1, c2 = _inputs(1500, 32, 7, 3); cu = torch.tensor([0, 1500], dtype=torch.int32, device='cuda');"
-        "a = c1.cuda().unsqueeze(0).requires_grad_(True); b = c2.cuda().unsqueeze(0).requires_grad_(True);"
-        "l = M.modularity_terms(h.cuda(), cu, 1500, a, b); (l[0,0] + l[0,1]).backward();"
-        "print('RES', l[0,0].item(), l[0,1].item(), a.grad.norm().item(), b.grad.norm().item(), a.grad[0,3,5].item())"
-    ) % (root, root)
-    outs = []
-    for sym in ("0", "1"):
-        env = dict(os.environ, IMP_MODULARITY_SYMMETRIC=sym)
-        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
-        assert r.returncode == 0, r.stderr[-2000:]
-        line = [ln for ln in r.stdout.splitlines() if ln.startswith("RES")][-1]
-        outs.append([float(x) for x in line.split()[1:]])
-    for x, y in zip(*outs):
-        assert abs(x - y) <= 2e-4 * abs(y) + 1e-6, outs
+def test_signed_features_use_the_gram_degrees():
+    """compute_modularity accepts any x (utils.py:205-228).  Behind path_net's ReLU the features are >= 0 and the
+    degrees come from the closed form d_i = xh_i.(sum_j xh_j) - |xh_i|^2; signed features must take the Gram sweep
+    with its relu (utils.py:194) instead.  Both paths are checked against the oracle on the same graph size."""
+    from imp_b200 import modularity as M
+    from oracle import imp_oracle as O
+    g = torch.Generator().manual_seed(11)
+    n, p = 700, 16
+    base = torch.randn(8, 256, generator=g)
+    mix = torch.randn(n, 8, generator=g)
+    x = (mix @ base + 0.3 * torch.randn(n, 256, generator=g)).bfloat16().float()   # signed, clustered: many negative cosines
+    c = torch.randn(p, 256, generator=g)
+    cd = c.cuda().unsqueeze(0).requires_grad_(True)
+    loss = M.compute_modularity(cd, x.cuda().unsqueeze(0))
+    loss.backward()
+    ref, dref = O.modularity(c, x, chunk=256)
+    assert abs(loss.item() - ref.item()) <= 1e-3 * abs(ref.item()) + ABS_TOL, (loss.item(), ref.item())
+    assert rel(cd.grad[0], dref) < 2e-3, rel(cd.grad[0], dref)
