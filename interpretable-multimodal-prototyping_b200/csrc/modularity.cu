@@ -616,9 +616,10 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     const int tb = it % kTBufs, ls = it % kLStages;
     if (driver) { ensure(it); poll(); }
     __syncwarp();
-    mbar_wait(&tfull[tb], (it / kTBufs) & 1);
+    // suspended waits: a warp that ran ahead must not spin away the issue slots of the warps it is waiting for
+    mbar_wait_idle(&tfull[tb], (it / kTBufs) & 1, 4000u);
     tc_fence_after();
-    mbar_wait(&lfull[ls], (it / kLStages) & 1);
+    mbar_wait_idle(&lfull[ls], (it / kLStages) & 1, 4000u);
     const uint8_t* st = s_l + (size_t)ls * kLStage;
     const float4* sL = reinterpret_cast<const float4*>(st) + hc * 4;               // [token][16 float4]: + token*16 + g
     const float4* sd = reinterpret_cast<const float4*>(st + kLBytes) + hc * 4;
