@@ -113,7 +113,7 @@ struct PoolFwdParams {
 };
 
 template <int PP, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, PP <= 32 ? 2 : 1)      // two CTAs per SM hide the per-tile barrier latency
 pool_fwd_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolFwdParams p) {
   constexpr int NT1 = PP / 16;              // score n-tiles per warp (column half)
   constexpr int MT = PP / 16;               // m-tiles of the weighted sum
@@ -308,7 +308,7 @@ struct PoolBwdParams {
 };
 
 template <int PP, int NB, bool DZ, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, (!DZ && NB == 1 && PP <= 32) ? 2 : 1)
 pool_bwd_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolBwdParams p) {
   constexpr int NCOL = 2 * NB * PP;           // stacked rows of G = columns of E
   constexpr int NGW = NB * PP / 16;           // prototype groups (8 wide) per warp
@@ -541,8 +541,8 @@ constexpr size_t bwd_smem() {
 void split_plan(int max_len, int B, int* nsplit, int* tiles_per_split) {
   const int tiles = max(1, (max_len + kTM - 1) / kTM);
   const int sms = imp_num_sms();
-  // aim for >= 2 waves of CTAs while keeping at least 8 tiles (256 KB of h) per CTA
-  int want = max(1, (2 * sms + B - 1) / B);
+  // aim for >= 2 waves of CTAs (two resident per SM) while keeping at least 8 tiles (256 KB of h) per CTA
+  int want = max(1, (4 * sms + B - 1) / B);
   int cap = max(1, tiles / 8);
   int ns = min(want, cap);
   ns = min(ns, 256);
@@ -601,8 +601,8 @@ int launch_pool_fwd(const bf16* h, int total_rows, const int* cu, int B, int max
   int rc = imp_make_tmap_2d(&tm, h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, total_rows, kD * 2, 64, kTM,
                             CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  if (PP == 16) rc = run_fwd<16, 4>(tm, p, B, st);
-  else if (PP == 32) rc = run_fwd<32, 4>(tm, p, B, st);
+  if (PP == 16) rc = run_fwd<16, 2>(tm, p, B, st);
+  else if (PP == 32) rc = run_fwd<32, 2>(tm, p, B, st);
   else rc = run_fwd<64, 4>(tm, p, B, st);
   if (rc) return rc;
   IMP_LAUNCH("pool_merge", st, pool_merge_kernel<<<dim3(P, B), kD, 0, st>>>(p.part_acc, p.part_ml, pooled, lse, P, PP, p.nsplit));
@@ -646,10 +646,10 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
   const bool DZ = dz != nullptr;
 #define IMP_BWD(PPv, NBv, DZv, STv) rc = run_bwd<PPv, NBv, DZv, STv>(tm, p, B, st)
   if (PP == 16) {
-    if (nblocks == 1) { if (DZ) IMP_BWD(16, 1, true, 4); else IMP_BWD(16, 1, false, 4); }
+    if (nblocks == 1) { if (DZ) IMP_BWD(16, 1, true, 4); else IMP_BWD(16, 1, false, 2); }
     else              { if (DZ) IMP_BWD(16, 2, true, 4); else IMP_BWD(16, 2, false, 4); }
   } else if (PP == 32) {
-    if (nblocks == 1) { if (DZ) IMP_BWD(32, 1, true, 4); else IMP_BWD(32, 1, false, 4); }
+    if (nblocks == 1) { if (DZ) IMP_BWD(32, 1, true, 4); else IMP_BWD(32, 1, false, 2); }
     else              { if (DZ) IMP_BWD(32, 2, true, 3); else IMP_BWD(32, 2, false, 3); }
   } else {
     if (DZ) IMP_BWD(64, 1, true, 3); else IMP_BWD(64, 1, false, 3);
