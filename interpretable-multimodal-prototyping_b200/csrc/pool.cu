@@ -525,6 +525,244 @@ __global__ void reduce_db_kernel(const float* __restrict__ part, float* __restri
   db[f] = accumulate ? db[f] + a : a;
 }
 
+// ------------------------------------------------------------------------------------------
+// dz pass on tcgen05:  dz = keep_scale * [h > 0] * (E . G),  E = [dS | a] per block from S = h . G^T
+//   G (NCOL x 256, bf16, 128-byte swizzled boxes of 64 features) stacks [q~_k ; dpooled_k] of the NB blocks and
+//   serves both MMAs from the same shared-memory image: K-major B operand of S = h G^T (M 128, N NCOL, K 256)
+//   and MN-major B operand of dh = E G (M 128, N 256, K NCOL).  Per 128-row tile of h:
+//     TMA h tile -> MMA1 -> epilogue 1 (TMEM S -> a = exp(S - lse), dS = a (dA - delta) -> E in smem, bf16)
+//                -> MMA2 -> epilogue 2 (TMEM dh -> ReLU/dropout mask from the h tile, in place) -> coalesced
+//     store of dz and the column sums for db1.  MMA1 of the next tile overlaps epilogue 2 of this one.
+//   Warps: 0-7 epilogue (thread = patch row, warp pair splits the columns), 8 TMA producer, 9 MMA issuer.
+// ------------------------------------------------------------------------------------------
+constexpr int kZM = 128;                         // patch rows per tile
+constexpr int kZTile = kZM * kD * 2;             // 64 KB: four [128][64] boxes
+constexpr int kZThreads = 10 * 32;
+__device__ __forceinline__ uint32_t box128_off(int row, int col) {   // [128 rows][64 cols] bf16 boxes, 128-B swizzle
+  return (uint32_t)((col >> 6) * (kZM * 128) + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4) + ((col & 7) << 1));
+}
+
+struct DzParams {
+  const int* cu;
+  const float* qt[2];      long long qt_stride[2];
+  const float* dpool[2];   long long dpool_stride[2];
+  const float* lse[2];     // (B,P)
+  const float* delta[2];   // (B,P)
+  float* part_db;          // (B*nsplit, 256) or null
+  bf16* dz;                // (R,256)
+  int P, nsplit, tiles_per_split;
+  int relu_mask;
+  float keep_scale;
+};
+
+template <int PP, int NB>
+constexpr size_t dz_smem() { return 1024 + (size_t)2 * NB * PP * 512 + (size_t)kZM * ((2 * NB * PP + 63) / 64) * 128 + 2 * kZTile + 2 * NB * PP * 4 + 256; }
+
+template <int PP, int NB>
+__global__ void __launch_bounds__(kZThreads, 1)
+pool_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const DzParams p) {
+  constexpr int NCOL = 2 * NB * PP;              // rows of G = columns of S and E
+  constexpr int EBOX = (NCOL + 63) / 64;
+  constexpr int NS = NB * PP / 2;                // prototype slots per epilogue thread (warp pair splits them)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* s_g = smem;                                        // G: 4 boxes [NCOL][64], box stride NCOL*128
+  uint8_t* s_e = s_g + NCOL * 512;                            // E: EBOX boxes [128][64]
+  uint8_t* tiles = s_e + EBOX * kZM * 128;                    // 2 x h tile
+  float* s_lse = reinterpret_cast<float*>(tiles + 2 * kZTile);
+  float* s_delta = s_lse + NB * PP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + NB * PP);
+  uint64_t* full = bars;          // [2] TMA -> MMA1
+  uint64_t* empty = bars + 2;     // [2] 8 epilogue warps -> TMA
+  uint64_t* sfull = bars + 4;     // MMA1 -> epilogue 1
+  uint64_t* sempty = bars + 5;    // 8 warps -> MMA1 (S consumed)
+  uint64_t* efull = bars + 6;     // 8 warps -> MMA2 (E written)
+  uint64_t* dfull = bars + 7;     // MMA2 -> epilogue 2
+  uint64_t* dempty = bars + 8;    // 8 warps -> MMA2 (dh consumed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int b = blockIdx.y, split = blockIdx.x;
+  const int row_begin = __ldg(p.cu + b), row_end = __ldg(p.cu + b + 1);
+  const int ntiles_bag = (row_end - row_begin + kZM - 1) / kZM;
+  const int t0 = split * p.tiles_per_split;
+  const int ntiles = max(0, min(ntiles_bag, t0 + p.tiles_per_split) - t0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (ntiles == 0) {
+    if (p.part_db)
+      for (int i = threadIdx.x; i < kD; i += kZThreads) p.part_db[((size_t)b * p.nsplit + split) * kD + i] = 0.f;
+    return;
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tm_h);
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+    mbar_init(sfull, 1); mbar_init(sempty, 8); mbar_init(efull, 8); mbar_init(dfull, 1); mbar_init(dempty, 8);
+    mbar_fence_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  // G = [q~_0 ; dpooled_0 ; q~_1 ; dpooled_1] as bf16 boxes (padded prototypes are zero rows)
+  for (int i = threadIdx.x; i < NCOL * 64; i += kZThreads) {
+    const int r = i >> 6, c = (i & 63) << 2;
+    const int blk = r / (2 * PP), within = r % (2 * PP), pi = within % PP;
+    const bool is_dp = within >= PP;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pi < p.P) {
+      const float* src = is_dp ? p.dpool[blk] + (size_t)b * p.dpool_stride[blk] : p.qt[blk] + (size_t)b * p.qt_stride[blk];
+      v = *reinterpret_cast<const float4*>(src + (size_t)pi * kD + c);
+    }
+    const uint32_t off = (uint32_t)((c >> 6) * (NCOL * 128) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
+    *reinterpret_cast<uint2*>(s_g + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+  for (int i = threadIdx.x; i < NB * PP; i += kZThreads) {
+    const int blk = i / PP, pi = i % PP;
+    s_lse[i] = pi < p.P ? p.lse[blk][(size_t)b * p.P + pi] : INFINITY;      // padded prototypes: a = 0
+    s_delta[i] = pi < p.P ? p.delta[blk][(size_t)b * p.P + pi] : 0.f;
+  }
+  fence_proxy_async_smem();                      // G was written by the generic proxy, the MMAs read it through the async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_s = tmem_base, tm_d = tmem_base + 128;
+
+  if (warp == 8) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      for (int i = 0; i < ntiles; ++i) {
+        const int stage = i & 1;
+        mbar_wait_idle(&empty[stage], ((i >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[stage], kZTile);
+        uint8_t* dst = tiles + (size_t)stage * kZTile;
+#pragma unroll
+        for (int bx = 0; bx < 4; ++bx)
+          tma_load_2d(dst + bx * (kZM * 128), &tm_h, &full[stage], bx * 64, row_begin + (t0 + i) * kZM);
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(kZM, NCOL, 0, 0);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(kZM, kD, 0, 1);
+      const uint32_t sg = smem_u32(s_g), se = smem_u32(s_e);
+      for (int i = 0; i < ntiles; ++i) {
+        const int stage = i & 1;
+        const uint32_t sh = smem_u32(tiles + (size_t)stage * kZTile);
+        mbar_wait_idle(&full[stage], (i >> 1) & 1);
+        mbar_wait_idle(sempty, (i & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) {       // S = h G^T, K = 256 features
+          const uint64_t ad = umma_desc_sw128(sh + (k >> 2) * (kZM * 128) + (k & 3) * 32, 0, 1024);
+          const uint64_t bd = umma_desc_sw128(sg + (k >> 2) * (NCOL * 128) + (k & 3) * 32, 0, 1024);
+          umma_f16(tm_s, ad, bd, idesc1, k != 0);
+        }
+        umma_commit(sfull);
+        mbar_wait_idle(efull, i & 1);
+        mbar_wait_idle(dempty, (i & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < NCOL / 16; ++k) {     // dh = E G, K = NCOL stacked prototype rows
+          const uint64_t ad = umma_desc_sw128(se + (k >> 2) * (kZM * 128) + (k & 3) * 32, 0, 1024);
+          // G as an MN-major B operand: 64-feature boxes are NCOL*128 bytes apart, 8 k-rows are 1024 bytes apart
+          const uint64_t bd = umma_desc_sw128(sg + k * 2048, NCOL * 128, 1024);
+          umma_f16(tm_d, ad, bd, idesc2, k != 0);
+        }
+        umma_commit(dfull);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue warps ------------------------------
+    const int q = warp & 3, hf = warp >> 2;
+    const int n = q * 32 + lane;                   // row inside the tile = TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const bool nm = p.relu_mask == 0;
+    const float keep = p.keep_scale;
+    float dbacc = 0.f;                             // column sum for feature f = threadIdx.x
+    for (int i = 0; i < ntiles; ++i) {
+      const int stage = i & 1;
+      uint8_t* tile = tiles + (size_t)stage * kZTile;
+      const int tile_row0 = row_begin + (t0 + i) * kZM;
+      const bool row_ok = tile_row0 + n < row_end;
+      // ---- epilogue 1: S -> E ----
+      mbar_wait(sfull, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c8 = 0; c8 < NS / 8; ++c8) {
+        const int slot0 = hf * NS + c8 * 8;        // prototype slots slot0..slot0+7 (never straddle a block: PP % 8 == 0)
+        const int blk = slot0 / PP, p0 = slot0 % PP;
+        const int cS = blk * 2 * PP + p0, cA = cS + PP;
+        uint32_t sv[8], av[8];
+        tmem_ld8(tm_s + lane_addr + cS, sv);
+        tmem_ld8(tm_s + lane_addr + cA, av);
+        tmem_ld_wait();
+        float a[8], ds[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float lse = s_lse[slot0 + e], dl = s_delta[slot0 + e];
+          a[e] = row_ok ? exp2f((__uint_as_float(sv[e]) - lse) * 1.4426950408889634f) : 0.f;
+          ds[e] = a[e] * (__uint_as_float(av[e]) - dl);
+        }
+        *reinterpret_cast<uint4*>(s_e + box128_off(n, cS)) =
+            make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
+        *reinterpret_cast<uint4*>(s_e + box128_off(n, cA)) =
+            make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();                    // E is read by MMA2 through the async proxy
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(sempty); mbar_arrive(efull); }
+      // ---- epilogue 2: dh -> dz (in place over the h tile) ----
+      mbar_wait(dfull, i & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        const int f0 = hf * 128 + cc * 32;
+        uint32_t v[32];
+        tmem_ld32(tm_d + lane_addr + f0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          uint4* ph = reinterpret_cast<uint4*>(tile + box128_off(n, f0 + g8 * 8));
+          const uint4 hv = *ph;
+          const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float z0 = (nm || bf16lo(hw[e]) > 0.f) ? __uint_as_float(v[g8 * 8 + 2 * e]) * keep : 0.f;
+            const float z1 = (nm || bf16hi(hw[e]) > 0.f) ? __uint_as_float(v[g8 * 8 + 2 * e + 1]) * keep : 0.f;
+            o[e] = pack_bf16x2(z0, z1);
+          }
+          *ph = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dempty);
+      bar_sync(1, 256);                            // the whole dz tile is in shared memory
+      const int nvalid = min(kZM, row_end - tile_row0);
+      for (int it = threadIdx.x; it < nvalid * 32; it += 256) {
+        const int r = it >> 5, c = (it & 31) << 3;
+        *reinterpret_cast<uint4*>(p.dz + (size_t)(tile_row0 + r) * kD + c) = *reinterpret_cast<const uint4*>(tile + box128_off(r, c));
+      }
+      if (p.part_db) {
+        const int f = threadIdx.x;
+        float acc = 0.f;
+        for (int r = 0; r < nvalid; ++r) acc += __bfloat162float(*reinterpret_cast<const bf16*>(tile + box128_off(r, f)));
+        dbacc += acc;
+      }
+      fence_proxy_async_smem();                    // generic-proxy writes of this stage before the next TMA load into it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+    }
+    if (p.part_db) p.part_db[((size_t)b * p.nsplit + split) * kD + threadIdx.x] = dbacc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 int pad_protos(int P) { return P <= 16 ? 16 : (P <= 32 ? 32 : 64); }
 
 template <int PP, int STAGES>
@@ -574,6 +812,27 @@ int run_bwd(const CUtensorMap& tm, const PoolBwdParams& p, int B, cudaStream_t s
   return IMP_OK;
 }
 
+template <int PP, int NB>
+int run_dz(const CUtensorMap& tm, const DzParams& p, int B, cudaStream_t st) {
+  constexpr size_t smem = dz_smem<PP, NB>();
+  static_assert(smem <= 227 * 1024, "pool_bwd_dz shared memory");
+  static bool done = false;
+  if (!done) {
+    IMP_CUDA(cudaFuncSetAttribute(pool_bwd_dz_kernel<PP, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done = true;
+  }
+  IMP_LAUNCH("pool_bwd_dz", st, pool_bwd_dz_kernel<PP, NB><<<dim3(p.nsplit, B), kZThreads, smem, st>>>(tm, p));
+  return IMP_OK;
+}
+
+// 128-row tiles, one CTA per SM: >= 2 waves of CTAs, at least 4 tiles (256 KB of h) per CTA
+void dz_split_plan(int max_len, int B, int* nsplit, int* tiles_per_split) {
+  const int tiles = max(1, (max_len + kZM - 1) / kZM);
+  int ns = max(1, min(min((2 * imp_num_sms() + B - 1) / B, max(1, tiles / 4)), 128));
+  *tiles_per_split = (tiles + ns - 1) / ns;
+  *nsplit = (tiles + *tiles_per_split - 1) / *tiles_per_split;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -613,7 +872,9 @@ size_t pool_bwd_workspace_bytes(int B, int max_len, int P) {
   int ns, tps;
   split_plan(max_len, B, &ns, &tps);
   const int PP = pad_protos(P);
-  return ((size_t)B * ns * PP * kD + (size_t)B * ns * kD) * sizeof(float);
+  int nz, tz;
+  dz_split_plan(max_len, B, &nz, &tz);
+  return ((size_t)B * ns * PP * kD + (size_t)B * nz * kD) * sizeof(float);
 }
 
 int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max_len, int nblocks,
@@ -637,28 +898,47 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
     p.lse[k] = lse[s]; p.delta[k] = delta[s];
   }
   p.part_dq = workspace;
-  p.part_db = (dz && db1) ? workspace + (size_t)B * p.nsplit * PP * kD : nullptr;
-  p.dz = dz;
+  p.part_db = nullptr;
+  p.dz = nullptr;
   CUtensorMap tm;
   int rc = imp_make_tmap_2d(&tm, h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, total_rows, kD * 2, 64, kTM,
                             CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  const bool DZ = dz != nullptr;
-#define IMP_BWD(PPv, NBv, DZv, STv) rc = run_bwd<PPv, NBv, DZv, STv>(tm, p, B, st)
-  if (PP == 16) {
-    if (nblocks == 1) { if (DZ) IMP_BWD(16, 1, true, 4); else IMP_BWD(16, 1, false, 2); }
-    else              { if (DZ) IMP_BWD(16, 2, true, 4); else IMP_BWD(16, 2, false, 4); }
-  } else if (PP == 32) {
-    if (nblocks == 1) { if (DZ) IMP_BWD(32, 1, true, 4); else IMP_BWD(32, 1, false, 2); }
-    else              { if (DZ) IMP_BWD(32, 2, true, 3); else IMP_BWD(32, 2, false, 3); }
-  } else {
-    if (DZ) IMP_BWD(64, 1, true, 3); else IMP_BWD(64, 1, false, 3);
-  }
+  // (1) dq~ of the requested block: streaming mma.sync kernel over that block alone
+  {
+    PoolBwdParams q1 = p;
+    q1.qt[0] = qt[dq_block]; q1.qt_stride[0] = qt_stride[dq_block];
+    q1.dpool[0] = dpool[dq_block]; q1.lse[0] = lse[dq_block]; q1.delta[0] = delta[dq_block];
+    q1.dq_block = 0;
+#define IMP_BWD(PPv, STv) rc = run_bwd<PPv, 1, false, STv>(tm, q1, B, st)
+    if (PP == 16) IMP_BWD(16, 2); else if (PP == 32) IMP_BWD(32, 2); else IMP_BWD(64, 3);
 #undef IMP_BWD
-  if (rc) return rc;
+    if (rc) return rc;
+  }
+  // (2) dz (and db1): both blocks at once on tcgen05
+  int nz = 0;
+  if (dz) {
+    DzParams z;
+    dz_split_plan(max_len, B, &z.nsplit, &z.tiles_per_split);
+    nz = z.nsplit;
+    z.cu = cu; z.P = P; z.relu_mask = relu_mask; z.keep_scale = relu_mask ? keep_scale : 1.f; z.dz = dz;
+    for (int k = 0; k < 2; ++k) {
+      z.qt[k] = p.qt[k]; z.qt_stride[k] = p.qt_stride[k]; z.dpool[k] = p.dpool[k]; z.dpool_stride[k] = p.dpool_stride[k];
+      z.lse[k] = p.lse[k]; z.delta[k] = p.delta[k];
+    }
+    z.part_db = db1 ? workspace + (size_t)B * p.nsplit * PP * kD : nullptr;
+    CUtensorMap tmz;
+    if ((rc = imp_make_tmap_2d(&tmz, h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, total_rows, kD * 2, 64, kZM,
+                               CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if (PP == 16) rc = nblocks == 1 ? run_dz<16, 1>(tmz, z, B, st) : run_dz<16, 2>(tmz, z, B, st);
+    else if (PP == 32) rc = nblocks == 1 ? run_dz<32, 1>(tmz, z, B, st) : run_dz<32, 2>(tmz, z, B, st);
+    else rc = run_dz<64, 1>(tmz, z, B, st);
+    if (rc) return rc;
+    p.part_db = z.part_db;
+  }
   IMP_LAUNCH("reduce_dq", st, reduce_dq_kernel<<<dim3(P, B), kD, 0, st>>>(p.part_dq, dq, P, PP, p.nsplit));
   if (p.part_db) {
-    IMP_LAUNCH("reduce_db", st, reduce_db_kernel<<<1, kD, 0, st>>>(p.part_db, db1, B * p.nsplit, db_accumulate));
+    IMP_LAUNCH("reduce_db", st, reduce_db_kernel<<<1, kD, 0, st>>>(p.part_db, db1, B * nz, db_accumulate));
   }
   return IMP_OK;
 }
