@@ -310,7 +310,7 @@ struct GramParams {
   const float* lfix;        // tiled, see lfix_index
   float* d;                 // (Rpad) degrees
   double* e;                // (B)
-  float* T;                 // (Rpad, PtPad) atomicAdd
+  float* T;                 // tiled like lfix, atomicAdd
   double* s;                // (B, 2 groups): sum_ij (A_ij/e - d_i d_j/e^2) delta_ij
   const int* negflag;       // (1) device flag: 1 when some element of h is negative (closed-form degrees do not apply)
   int tiles_per_split;      // column tiles per CTA
@@ -723,7 +723,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     const int r = idx & (kBM - 1), k = idx >> 7;
     const float* src = s_T + (size_t)k * kSwThreads + r;
     const float t = (src[0] + src[kBM]) + (src[2 * kBM] + src[3 * kBM]);
-    if (t != 0.f && i0 + r < row_end) atomicAdd(p.T + (size_t)(i0 + r) * PtPad + k, t);
+    if (t != 0.f && i0 + r < row_end) atomicAdd(p.T + lfix_index(i0 + r, k, PtPad), t);      // tiled like L: coalesced REDs
   }
   tc_fence_before();
   __syncthreads();
@@ -768,10 +768,10 @@ __global__ void __launch_bounds__(256) modularity_finish_kernel(const FinishPara
     const int nr = min(32, r1 - rb);
     __syncthreads();
     for (int idx = f; idx < 32 * PTPAD; idx += 256) {
-      const int r = idx / PTPAD, k = idx % PTPAD;
+      const int r = idx & 31, k = idx >> 5;          // rows fastest: T and L are tiled [tile][slot][64 rows]
       float v = 0.f;
       if (r < nr) {
-        const float t = p.T[(size_t)(rb + r) * PTPAD + k];
+        const float t = p.T[lfix_index(rb + r, k, PTPAD)];
         if (t != 0.f) {
           const int nfix = (int)p.lfix[lfix_index(rb + r, k, PTPAD)] >> 5;
           const float c = ex2_approx((float)kCOff - (float)nfix * (1.f / (float)(1 << kLogShift)));
@@ -857,7 +857,7 @@ Carve carve(void* ws, int total_rows, int B, int PtPad) {
   c.lfix = reinterpret_cast<float*>(base + off); off += up(ntile * PtPad * 64 * 4);
   c.zero_off = off;
   c.d = reinterpret_cast<float*>(base + off); off += up(rpad * 4);
-  c.T = reinterpret_cast<float*>(base + off); off += up(rpad * PtPad * 4);
+  c.T = reinterpret_cast<float*>(base + off); off += up(ntile * PtPad * 64 * 4);
   c.e = reinterpret_cast<double*>(base + off); off += up((size_t)B * 8);
   c.s = reinterpret_cast<double*>(base + off); off += up((size_t)B * 2 * 8);
   c.colsum = reinterpret_cast<float*>(base + off); off += up((size_t)B * kD * 4);
