@@ -29,6 +29,9 @@ sys.path.insert(0, ROOT)
 N_PATCH, D_IN, N_PROTO, N_PATHWAYS = 16384, 512, 32, 6
 GROUP_SIZES = [82, 330, 513, 440, 1538, 451]
 WORKLOAD = "configs[1]: survival training, synthetic TCGA-shaped bags 16384x512, 32 prototypes, 6 pathways, bf16"
+# dram__bytes_read.sum + dram__bytes_write.sum of one modularity_sweep launch from `ncu --set full`
+# (profiles/r01_ncu_full_final.md), keyed by bags per launch; None when not captured for that size
+SWEEP_TRAFFIC_PER_LAUNCH = {32: 424.2e6 + 61.9e6}
 
 
 def parse():
@@ -276,9 +279,20 @@ def run_ours(args):
     roofline = {"kernel": dom.get("kernel"), "bound": dom.get("bound", "hbm"), "achieved": dom.get("achieved"),
                 "peak": dom.get("peak"), "unit": dom.get("unit"), "frac": dom.get("frac"), "traffic": None,
                 "peak_source": peak_src + " (MEASURED_PEAKS.json, sustained bf16 / copy bandwidth)",
-                "note": "dominant kernel of the training step is the modularity sweep: tcgen05 Gram tiles feed an integer "
-                        "add-max (VIADDMNMX) contraction over tokens on the ALU pipe, which is what bounds it; "
-                        "'achieved' counts only the Gram FLOPs"}
+                "note": "dominant kernel of the training step is the modularity pair sweep: tcgen05 Gram tiles (the FLOPs counted "
+                        "in 'achieved') feed a (min,+) contraction over the 40 token slots plus a tanh/gradient tail on the CUDA "
+                        "cores; it is issue-bound there (see 'cuda_core_issue'), not tensor- or HBM-bound"}
+    if dom.get("kernel") == "modularity_sweep":
+        pairs = float(B) * N * N
+        t = pk["modularity_sweep"]["avg_ms"] * 1e-3
+        clk = (clocks or {}).get("sm_mhz") or 1965.0
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        roofline["cuda_core_issue"] = {
+            "pairs_per_s": pairs / t, "token_pair_evals_per_s": pairs * (P + N_PATHWAYS + 1) / t,
+            "sm_cycles_per_32_pairs": t * clk * 1e6 * sm_count * 4 / (pairs / 32),
+            "warp_instructions_per_32_pairs": 94, "what": "cycles of one scheduler sub-partition per warp of 32 pairs; "
+            "94 instructions at 1 IPC would be the issue roofline (profiles/r01_sweep_iterations.md)"}
+        roofline["traffic"] = SWEEP_TRAFFIC_PER_LAUNCH.get(B)
     # fused streaming path (the metric's 'fused-kernel HBM GB/s'): x read once forward + once backward
     stream_names = ["pathnet_fwd", "pool_fwd", "pool_merge", "pool_bwd_dq", "pool_bwd_dz", "reduce_dq", "reduce_db", "pathnet_dw",
                     "sum_partials", "cast_bf16"]

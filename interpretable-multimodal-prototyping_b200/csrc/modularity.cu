@@ -781,16 +781,24 @@ __global__ void __launch_bounds__(256) modularity_finish_kernel(const FinishPara
       s_dc[r][k] = v;
     }
     __syncthreads();
-    for (int r = 0; r < nr; ++r) {
-      const float xv = __bfloat162float(p.h[(size_t)(rb + r) * kD + f]) * __ldg(p.invn + rb + r);
-      const float4* dc4 = reinterpret_cast<const float4*>(&s_dc[r][0]);
+    for (int r8 = 0; r8 < nr; r8 += 8) {            // 8 independent global loads in flight per thread
+      float xv[8];
 #pragma unroll
-      for (int k4 = 0; k4 < PTPAD / 4; ++k4) {
-        const float4 dcv = dc4[k4];
-        acc[4 * k4 + 0] = fmaf(dcv.x, xv, acc[4 * k4 + 0]);
-        acc[4 * k4 + 1] = fmaf(dcv.y, xv, acc[4 * k4 + 1]);
-        acc[4 * k4 + 2] = fmaf(dcv.z, xv, acc[4 * k4 + 2]);
-        acc[4 * k4 + 3] = fmaf(dcv.w, xv, acc[4 * k4 + 3]);
+      for (int j = 0; j < 8; ++j) {
+        const int r = r8 + j;
+        xv[j] = r < nr ? __bfloat162float(p.h[(size_t)(rb + r) * kD + f]) * __ldg(p.invn + rb + r) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4* dc4 = reinterpret_cast<const float4*>(&s_dc[r8 + j][0]);     // rows >= nr hold zeros
+#pragma unroll
+        for (int k4 = 0; k4 < PTPAD / 4; ++k4) {
+          const float4 dcv = dc4[k4];
+          acc[4 * k4 + 0] = fmaf(dcv.x, xv[j], acc[4 * k4 + 0]);
+          acc[4 * k4 + 1] = fmaf(dcv.y, xv[j], acc[4 * k4 + 1]);
+          acc[4 * k4 + 2] = fmaf(dcv.z, xv[j], acc[4 * k4 + 2]);
+          acc[4 * k4 + 3] = fmaf(dcv.w, xv[j], acc[4 * k4 + 3]);
+        }
       }
     }
   }
