@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--protos", type=int, default=N_PROTO)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="report the eager (Python-launched) steps instead of CUDA-graph replays")
     ap.add_argument("--workload", default="fusion", choices=["fusion", "kmeans"],
                     help="fusion: the headline (configs[1]); kmeans: configs[4], 2^20 x 512 fp32 -> 32 centroids, one assignment pass per step")
     return ap.parse_args()
@@ -246,6 +247,33 @@ def run_ours(args):
     ms_s, recs_s, _, _ = timed(lambda: one_step(batch, cot_p, cot_o, False), args.steps, args.warmup, profile=True)
     value_s = world * B * args.steps / (ms_s * 1e-3)
 
+    # ---- the same two steps captured in CUDA graphs (what a deployment replays; the eager numbers above carry
+    #      the per-kernel event timing).  world > 1: the NCCL all-reduce stays outside the graph. ----
+    eager = {"value": value, "ms_per_step": ms / args.steps, "streaming_only_value": value_s,
+             "streaming_only_ms_per_step": ms_s / args.steps}
+    graph_note = "training and streaming-only steps replayed from CUDA graphs (step.GraphedStep); 'eager' = same steps launched from Python"
+    if not args.no_graph:
+        try:
+            def graphed(with_mod):
+                runner.with_modularity = with_mod
+                gs = S.GraphedStep(runner).capture(batch, cot_p, cot_o)
+
+                def fn():
+                    gs.replay()
+                    if world > 1:
+                        S.allreduce_gradients(runner, world)
+                m, _, _, _ = timed(fn, args.steps, args.warmup)
+                gs.close()
+                return m
+            ms = graphed(True)
+            ms_s = graphed(False)
+            value = world * B * args.steps / (ms * 1e-3)
+            value_s = world * B * args.steps / (ms_s * 1e-3)
+        except Exception as exc:                      # keep the eager measurement, say why
+            graph_note = "CUDA-graph capture unavailable (%s: %s); eager numbers reported" % (type(exc).__name__, str(exc)[:200])
+    else:
+        graph_note = "eager launches (--no-graph)"
+
     # ---- per-kernel roofline from the event-bracketed launches of the timed region ----
     def per_kernel(records, steps):
         agg = {}
@@ -376,6 +404,7 @@ def run_ours(args):
                        "parallelism": "dp%d" % world},
             "streaming_only": {"value": value_s, "unit": "bags/s", "ms_per_step": ms_s / args.steps,
                                "what": "same step without the O(N^2) modularity term"},
+            "launch_mode": graph_note, "eager": eager,
             "roofline": roofline, "roofline_streaming": roofline_stream, "kernels": kernels_out,
             "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
         }

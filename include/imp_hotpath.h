@@ -39,6 +39,11 @@ int imp_profile_collect(const char** names, float* ms, int max_records);
 int imp_pathnet_fwd(const void* x, const void* w1, const float* b1, void* h, int rows, int in_features,
                     float p_drop, unsigned seed, void* stream);
 
+/* Optional device word XOR-ed into the seed of every dropout kernel (path_net, omic encoders) at run time;
+ * NULL (the default) disables it.  A captured CUDA graph bakes `seed` arguments in; advancing this word inside
+ * the graph gives every replay a fresh keep-mask (umeml_gan.py:267 draws a new mask per step). */
+int imp_set_seed_offset(const unsigned* device_word);
+
 /* backward of A1 wrt W1: dw1 (256,in_features) fp32 (+)= dz^T x, dz (rows,256) bf16.   autograd of :266 */
 size_t imp_pathnet_dw_workspace_bytes(int in_features);
 int imp_pathnet_dw(const void* dz, const void* x, float* dw1, void* workspace, int rows, int in_features,

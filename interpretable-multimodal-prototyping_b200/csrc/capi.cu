@@ -118,6 +118,13 @@ extern "C" int imp_profile_collect(const char** names, float* ms, int max_record
   return n;
 }
 
+static std::atomic<const uint32_t*> g_seed_offset{nullptr};
+const uint32_t* imp_seed_offset_ptr() { return g_seed_offset.load(); }
+extern "C" int imp_set_seed_offset(const unsigned* device_word) {
+  g_seed_offset.store(device_word);
+  return IMP_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // A1 path_net
 // ------------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@ struct OmicParams {
   int B, G, K;
   float keep_scale;
   uint32_t drop_thresh, seed;
+  const uint32_t* seed_offset;    // device word XOR-ed into the seed, or null
 };
 
 __device__ __forceinline__ float gather_gene(const OmicParams& p, int b, int gene) {
@@ -66,7 +67,8 @@ __global__ void __launch_bounds__(256) omic_fwd_kernel(const OmicParams p) {
     v = fmaxf(v + __ldg(p.bias[k] + f), 0.f);
     const int b = b0 + lane;
     if (p.drop_thresh) {
-      const uint32_t hsh = mix32(p.seed ^ (((uint32_t)(b * p.K + k) * 256u + (uint32_t)f) * 0x9E3779B1u));
+      const uint32_t seed = p.seed ^ (p.seed_offset ? __ldg(p.seed_offset) : 0u);
+      const uint32_t hsh = mix32(seed ^ (((uint32_t)(b * p.K + k) * 256u + (uint32_t)f) * 0x9E3779B1u));
       v = ((hsh & 0xffu) >= p.drop_thresh) ? v * p.keep_scale : 0.f;
     }
     p.out[((size_t)b * p.K + k) * kD + f] = v;
@@ -168,7 +170,7 @@ static int fill_params(OmicParams& p, const float* x, const int* mask, const flo
   if (K < 1 || K > kMaxGroups) IMP_FAIL(IMP_ERR_ARG, "omic: %d gene groups (1..%d supported)", K, kMaxGroups);
   if (B <= 0 || G <= 0) IMP_FAIL(IMP_ERR_ARG, "omic: bad shape B=%d G=%d", B, G);
   if (p_drop < 0.f || p_drop >= 1.f) IMP_FAIL(IMP_ERR_ARG, "omic: p_drop %f out of [0,1)", p_drop);
-  p.x = x; p.mask = mask; p.means = means; p.idx = idx; p.B = B; p.G = G; p.K = K; p.seed = seed;
+  p.x = x; p.mask = mask; p.means = means; p.idx = idx; p.B = B; p.G = G; p.K = K; p.seed = seed; p.seed_offset = imp_seed_offset_ptr();
   for (int k = 0; k <= K; ++k) p.goff[k] = group_offsets[k];
   for (int k = 0; k < K; ++k)
     if (p.goff[k + 1] <= p.goff[k]) IMP_FAIL(IMP_ERR_ARG, "omic: group %d is empty", k);

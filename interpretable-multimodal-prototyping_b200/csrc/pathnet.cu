@@ -30,6 +30,7 @@ struct FwdParams {
   float keep_scale;       // 1/(1-p)
   uint32_t drop_thresh;   // keep element iff (hash byte) >= drop_thresh ; 0 => no dropout
   uint32_t seed;
+  const uint32_t* seed_offset;   // device word XOR-ed into the seed, or null
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
@@ -48,6 +49,7 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = p.kdim / kBK;
+  const uint32_t seed = p.seed ^ (p.seed_offset ? __ldg(p.seed_offset) : 0u);
 
   if (threadIdx.x < 256) s_bias[threadIdx.x] = p.bias[threadIdx.x];
   if (warp == kEpiWarps && lane == 0) {
@@ -130,7 +132,7 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #pragma unroll
           for (int e = 0; e < 4; ++e) f[e] = fmaxf(__uint_as_float(v[j + e]) + s_bias[col0 + j + e], 0.f);
           if (p.drop_thresh) {
-            uint32_t hsh = mix32(p.seed ^ ((uint32_t)row * 64u + (uint32_t)((col0 + j) >> 2)) * 0x9E3779B1u);
+            uint32_t hsh = mix32(seed ^ ((uint32_t)row * 64u + (uint32_t)((col0 + j) >> 2)) * 0x9E3779B1u);
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               f[e] = (((hsh >> (8 * e)) & 0xffu) >= p.drop_thresh) ? f[e] * p.keep_scale : 0.f;
@@ -318,6 +320,7 @@ int launch_pathnet_fwd(const bf16* x, const bf16* w1, const float* b1, bf16* h, 
   p.drop_thresh = (uint32_t)(p_drop * 256.f + 0.5f);
   p.keep_scale = p.drop_thresh ? 256.f / (256.f - (float)p.drop_thresh) : 1.f;
   p.seed = seed;
+  p.seed_offset = imp_seed_offset_ptr();
   static bool attr_done = false;
   if (!attr_done) {
     IMP_CUDA(cudaFuncSetAttribute(pathnet_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));

@@ -39,6 +39,66 @@ class HotPathStep(nn.Module):
         return loss
 
 
+class GraphedStep:
+    """The whole forward + backward of a fixed-shape batch captured once in a CUDA graph and replayed: the
+    hot path launches ~100 of its own kernels plus ~200 tiny cuBLAS/ATen kernels of the token algebra per step,
+    and the host cannot issue them as fast as the GPU runs them once the O(N^2) term is off.
+
+    The input tensors given to ``capture`` are static: refill them in place (``copy_``) between replays.
+    Dropout: the seeds passed by value are baked into the graph, so the graph advances a device word that
+    every dropout kernel XORs into its seed (``imp_set_seed_offset``) -- each replay draws a new mask.
+    Gradients land in ``param.grad`` of the wrapped module (tensors owned by the graph's memory pool)."""
+
+    def __init__(self, runner: HotPathStep):
+        self.runner = runner
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.loss: Optional[torch.Tensor] = None
+        self._seed_word: Optional[torch.Tensor] = None
+
+    def capture(self, batch: Dict, cot_proto: torch.Tensor, cot_omic: Optional[torch.Tensor], lengths=None,
+                warmup: int = 3) -> "GraphedStep":
+        from . import _lib
+        import ctypes
+        dev = cot_proto.device
+        params = [p for p in self.runner.parameters()]
+        self._seed_word = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.call("imp_set_seed_offset", self._seed_word)
+        _lib.profile_enable(False)
+
+        def body():
+            for p in params:
+                p.grad = None
+            self._seed_word.add_(0x61C88647)                      # new keep-masks on every replay
+            loss = self.runner(batch, cot_proto, cot_omic, lengths)
+            loss.backward()
+            return loss
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                              # warm-up off the capture stream (allocator, attributes)
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = body()
+        self._params = params
+        self._grads = [p.grad for p in params]
+        return self
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        for p, g in zip(self._params, self._grads):              # another capture may have re-bound .grad
+            p.grad = g
+        return self.loss
+
+    def close(self) -> None:
+        from . import _lib
+        _lib.call("imp_set_seed_offset", None)
+        self.graph = None
+
+
 def allreduce_gradients(module: nn.Module, world_size: int) -> None:
     """Mean of the per-rank gradients in one flat bucket (NCCL over NVLink; gloo in CPU tests)."""
     import torch.distributed as dist
