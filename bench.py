@@ -460,6 +460,12 @@ def run_kmeans(args):
 
 def main():
     args = parse()
+    # Exactly one line on stdout: libraries (NCCL prints its version banner there) write to fd 1 behind Python's
+    # back, so fd 1 is pointed at stderr for the run and the JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.workload == "kmeans":
         run_kmeans(args)
     elif args.impl == "reference":
