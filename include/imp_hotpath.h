@@ -105,6 +105,24 @@ int imp_modularity(const void* h, int total_rows, const int* cu_seqlens, int n_b
                    const float* chat, int n_tok1, int n_tok2, float temp, void* workspace, float* loss,
                    float* dchat, void* stream);
 
+/* The same computation for ONE bag whose patches are sharded over ranks by rows (multi-GPU giant bag, SURVEY.md
+ * 8(e); no reference counterpart).  Every rank allocates the full workspace and runs
+ *   imp_modularity_prepare  on its rows [row_offset, row_offset+local_rows) (row_offset % 64 == 0; h_local points
+ *                           at its first row): zeroes the accumulators, writes its part of the sections below;
+ *   collectives by the caller: exchange the row ranges of sections 0 (xh, 512 B per row) and 1 (fixed-point
+ *                           assignments, n_slot*256 B per 64-row tile, n_slot = sizes[1]/tiles), SUM-all-reduce
+ *                           section 2 (column sums, n_bags*256 floats), MAX-all-reduce section 3 (sign flag, 1 int);
+ *   imp_modularity_execute  degrees over all rows, pair sweep and token gradients of its rows against all columns:
+ *                           loss (n_bags,2) and dchat are PARTIAL sums the caller SUM-all-reduces.
+ * imp_modularity_sections returns byte offsets / sizes of the four sections inside the workspace (HOST arrays of 4).
+ * With row_offset = 0 and local_rows = total_rows the two calls are exactly imp_modularity (any n_bags). */
+int imp_modularity_sections(int total_rows, int n_bags, int n_tok1, int n_tok2, size_t* offsets, size_t* sizes);
+int imp_modularity_prepare(const void* h_local, int local_rows, int row_offset, int total_rows, const int* cu_seqlens,
+                           int n_bags, const float* chat, int n_tok1, int n_tok2, void* workspace, void* stream);
+int imp_modularity_execute(const void* h_local, int local_rows, int row_offset, int total_rows, const int* cu_seqlens,
+                           int n_bags, int max_len, int n_tok1, int n_tok2, float temp, void* workspace, float* loss,
+                           float* dchat, void* stream);
+
 /* A7  per-pathway omic encoders: medmm/modeling/models/umeml_gan.py:274-283,413-419, with the
  * feature-level imputation of :391-392 fused into the gather.
  * x_omic (batch,n_genes) fp32; insample_mask (batch,n_genes) int32 or NULL (1 = gene missing, its

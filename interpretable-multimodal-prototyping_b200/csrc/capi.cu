@@ -202,6 +202,27 @@ extern "C" int imp_modularity(const void* h, int total_rows, const int* cu_seqle
                            workspace, loss, dchat, ST(stream));
 }
 
+// multi-GPU giant bag: the same computation in two phases around the caller's collectives
+extern "C" int imp_modularity_sections(int total_rows, int n_bags, int n_tok1, int n_tok2, size_t* offsets, size_t* sizes) {
+  if (!offsets || !sizes) IMP_FAIL(IMP_ERR_ARG, "imp_modularity_sections: null pointer");
+  modularity_workspace_sections(total_rows, n_bags, n_tok1, n_tok2, offsets, sizes);
+  return IMP_OK;
+}
+extern "C" int imp_modularity_prepare(const void* h_local, int local_rows, int row_offset, int total_rows,
+                                      const int* cu_seqlens, int n_bags, const float* chat, int n_tok1, int n_tok2,
+                                      void* workspace, void* stream) {
+  if ((!h_local && local_rows > 0) || !cu_seqlens || !chat || !workspace) IMP_FAIL(IMP_ERR_ARG, "imp_modularity_prepare: null pointer");
+  return launch_modularity_prepare((const bf16*)h_local, local_rows, row_offset, total_rows, cu_seqlens, n_bags, chat,
+                                   n_tok1, n_tok2, workspace, ST(stream));
+}
+extern "C" int imp_modularity_execute(const void* h_local, int local_rows, int row_offset, int total_rows,
+                                      const int* cu_seqlens, int n_bags, int max_len, int n_tok1, int n_tok2, float temp,
+                                      void* workspace, float* loss, float* dchat, void* stream) {
+  if ((!h_local && local_rows > 0) || !cu_seqlens || !workspace || !loss || !dchat) IMP_FAIL(IMP_ERR_ARG, "imp_modularity_execute: null pointer");
+  return launch_modularity_execute((const bf16*)h_local, local_rows, row_offset, total_rows, cu_seqlens, n_bags, max_len,
+                                   n_tok1, n_tok2, temp, workspace, loss, dchat, ST(stream));
+}
+
 // ------------------------------------------------------------------------------------------
 // A7 per-pathway omic encoders, A8 missing-omics handling
 // ------------------------------------------------------------------------------------------

@@ -30,6 +30,12 @@ int launch_cast_bf16(const float* src, bf16* dst, size_t n, cudaStream_t st);
 size_t modularity_workspace_bytes(int total_rows, int B, int P1, int P2);
 int launch_modularity(const bf16* h, int total_rows, const int* cu, int B, int max_len, const float* chat, int P1, int P2,
                       float temp, void* workspace, float* loss, float* dchat, cudaStream_t st);
+void modularity_workspace_sections(int total_rows, int B, int P1, int P2, size_t* offsets, size_t* sizes);
+int launch_modularity_prepare(const bf16* h_local, int local_rows, int row_lo, int total_rows, const int* cu, int B,
+                              const float* chat, int P1, int P2, void* workspace, cudaStream_t st);
+int launch_modularity_execute(const bf16* h_local, int local_rows, int row_lo, int total_rows, const int* cu, int B,
+                              int max_len, int P1, int P2, float temp, void* workspace, float* loss, float* dchat,
+                              cudaStream_t st);
 
 // omic.cu
 int launch_omic_fwd(const float* x, const int* mask, const float* means, const int* idx, const int* group_offsets,

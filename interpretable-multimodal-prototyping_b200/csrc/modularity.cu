@@ -127,6 +127,7 @@ struct PrepParams {
   float* colsum;            // (B,256)  sum_j xh_j (bf16-rounded values)
   int* negflag;             // (1) set to 1 when any element of h is negative
   int R, B, P1, P2, P1pad;
+  int row_lo, row_hi;       // this call covers global rows [row_lo, row_hi) (row_lo % 64 == 0); h points at row row_lo
 };
 constexpr int kXsStride = kD + 4;        // fp32 row stride in smem: 16-byte skew per row (conflict-free float4 reads)
 
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(256) modularity_prep_kernel(const PrepParams p
   extern __shared__ float s_prep[];
   float* xs = s_prep;                             // [64][kXsStride]
   float* cs = xs + 64 * kXsStride;                // [PTPAD][kXsStride]
-  const int r0 = blockIdx.x * 64;
+  const int r0 = p.row_lo + blockIdx.x * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // ---------------- phase A ----------------
   bool neg = false;
@@ -147,8 +148,8 @@ __global__ void __launch_bounds__(256) modularity_prep_kernel(const PrepParams p
   for (int rr = 0; rr < 8; ++rr) {
     const int rl = warp * 8 + rr, row = r0 + rl;
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (row < p.R) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(p.h + (size_t)row * kD + lane * 8);
+    if (row < p.row_hi) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(p.h + (size_t)(row - p.row_lo) * kD + lane * 8);
       v[0] = bf16lo(raw.x); v[1] = bf16hi(raw.x); v[2] = bf16lo(raw.y); v[3] = bf16hi(raw.y);
       v[4] = bf16lo(raw.z); v[5] = bf16hi(raw.z); v[6] = bf16lo(raw.w); v[7] = bf16hi(raw.w);
     }
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(256) modularity_prep_kernel(const PrepParams p
     for (int k = 0; k < 8; ++k) v[k] *= inv;
     *reinterpret_cast<float4*>(xs + rl * kXsStride + lane * 8) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(xs + rl * kXsStride + lane * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    if (row < p.R) {
+    if (row < p.row_hi) {
       uint4 o;
       o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
       o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(256) modularity_prep_kernel(const PrepParams p
   // ---------------- phase B ----------------
   const int tg = threadIdx.x & 7, rg = threadIdx.x >> 3;        // token slots tg*TPG.., rows 2rg, 2rg+1
   const int Pt = p.P1 + p.P2;
-  const int tile_end = min(r0 + 64, p.R);
+  const int tile_end = min(r0 + 64, p.row_hi);
   int b = find_segment(p.cu, p.B, r0);
   for (; b < p.B; ++b) {
     const int sa = max(__ldg(p.cu + b), r0), sb = min(__ldg(p.cu + b + 1), tile_end);
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(256) modularity_prep_kernel(const PrepParams p
     }
   }
   // rows of the tile past the end of the data keep the sweep's loads finite
-  if (r0 + 64 > p.R) {
+  if (p.row_hi == p.R && r0 + 64 > p.R) {
     for (int i = threadIdx.x; i < PTPAD * 64; i += 256) {
       const int slot = i >> 6, rl = i & 63;
       if (r0 + rl >= p.R) p.lfix[lfix_index(r0 + rl, slot, PTPAD)] = (float)(kNMax * 32);
@@ -315,6 +316,7 @@ struct GramParams {
   const int* negflag;       // (1) device flag: 1 when some element of h is negative (closed-form degrees do not apply)
   int tiles_per_split;      // column tiles per CTA
   float inv_temp;
+  int row_lo, row_hi;       // rows owned by this call (sharded bag: this rank's row blocks); [0, INT_MAX) otherwise
 };
 
 constexpr size_t kDegSmem = 1024 + kABytes + kStages * kBBytes + 256;
@@ -504,8 +506,9 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
 
   const int b = blockIdx.z;
   const int row_begin = __ldg(p.cu + b), row_end = __ldg(p.cu + b + 1);
-  const int i0 = row_begin + blockIdx.x * kBM;
-  if (i0 >= row_end) return;
+  const int own_end = min(row_end, p.row_hi);                           // rows of this call: [max(row_begin,row_lo), own_end)
+  const int i0 = max(row_begin, p.row_lo) + blockIdx.x * kBM;
+  if (i0 >= own_end) return;
   const int ta0 = row_begin >> 6, ta1 = (row_end + kBN - 1) >> 6;        // absolute column tiles of the bag
   const int t0 = ta0 + blockIdx.y * p.tiles_per_split;
   const int ntiles = max(0, min(ta1, t0 + p.tiles_per_split) - t0);
@@ -590,7 +593,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   const int q = warp & 3, hc = warp >> 2;
   const int tid = threadIdx.x;                         // = hc*128 + row in block
   const int i = i0 + q * 32 + lane;
-  const bool row_ok = i < row_end;
+  const bool row_ok = i < own_end;
   float* myT = s_T + tid;                              // element p at myT[p * 512]
   float Li[PtPad];                                     // row operand: 2^23 + (N_i << 5)
 #pragma unroll
@@ -625,7 +628,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     const float4* sd = reinterpret_cast<const float4*>(st + kLBytes) + hc * 4;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + tb * kBN + hc * 16;
     const int jt0 = (t0 + it) * kBN;
-    const bool interior = (i0 + kBM <= row_end) && (jt0 >= row_begin) && (jt0 + kBN <= row_end) &&
+    const bool interior = (i0 + kBM <= own_end) && (jt0 >= row_begin) && (jt0 + kBN <= row_end) &&
                           (jt0 >= i0 + kBM || jt0 + kBN <= i0);
 
     auto group4 = [&](int g, auto interior_tag) {
@@ -723,7 +726,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     const int r = idx & (kBM - 1), k = idx >> 7;
     const float* src = s_T + (size_t)k * kSwThreads + r;
     const float t = (src[0] + src[kBM]) + (src[2 * kBM] + src[3 * kBM]);
-    if (t != 0.f && i0 + r < row_end) atomicAdd(p.T + lfix_index(i0 + r, k, PtPad), t);      // tiled like L: coalesced REDs
+    if (t != 0.f && i0 + r < own_end) atomicAdd(p.T + lfix_index(i0 + r, k, PtPad), t);      // tiled like L: coalesced REDs
   }
   tc_fence_before();
   __syncthreads();
@@ -747,6 +750,8 @@ struct FinishParams {
   float* dchat;       // (B, Pt, 256), zeroed by the launcher
   float* loss;        // (B, 2)
   int P1, P2, P1pad, rows_per_cta;
+  int row_lo, row_hi;       // rows owned by this call; h points at global row h_row0
+  int h_row0;
 };
 
 template <int PTPAD>
@@ -758,8 +763,8 @@ __global__ void __launch_bounds__(256) modularity_finish_kernel(const FinishPara
   if (blockIdx.x == 0 && f < 2) {
     p.loss[b * 2 + f] = (float)(-100.0 * p.s[(size_t)b * 2 + f]);          // utils.py:222-228: -100 tr((W/e) delta)
   }
-  const int r0 = row_begin + blockIdx.x * p.rows_per_cta;
-  const int r1 = min(row_end, r0 + p.rows_per_cta);
+  const int r0 = max(row_begin, p.row_lo) + blockIdx.x * p.rows_per_cta;
+  const int r1 = min(min(row_end, p.row_hi), r0 + p.rows_per_cta);
   if (r0 >= r1) return;
   float acc[PTPAD];
 #pragma unroll
@@ -786,7 +791,7 @@ __global__ void __launch_bounds__(256) modularity_finish_kernel(const FinishPara
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int r = r8 + j;
-        xv[j] = r < nr ? __bfloat162float(p.h[(size_t)(rb + r) * kD + f]) * __ldg(p.invn + rb + r) : 0.f;
+        xv[j] = r < nr ? __bfloat162float(p.h[(size_t)(rb + r - p.h_row0) * kD + f]) * __ldg(p.invn + rb + r) : 0.f;
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -845,7 +850,7 @@ int run_prep(const PrepParams& pp, cudaStream_t st) {
     IMP_CUDA(cudaFuncSetAttribute(modularity_prep_kernel<PTPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done = true;
   }
-  IMP_LAUNCH("modularity_prep", st, modularity_prep_kernel<PTPAD><<<(pp.R + 63) / 64, 256, smem, st>>>(pp));
+  IMP_LAUNCH("modularity_prep", st, modularity_prep_kernel<PTPAD><<<(pp.row_hi - pp.row_lo + 63) / 64, 256, smem, st>>>(pp));
   return IMP_OK;
 }
 
@@ -882,25 +887,50 @@ size_t modularity_workspace_bytes(int total_rows, int B, int P1, int P2) {
   return carve(nullptr, total_rows, B, PtPad).total + 256;
 }
 
-int launch_modularity(const bf16* h, int total_rows, const int* cu, int B, int max_len, const float* chat, int P1, int P2,
-                      float temp, void* workspace, float* loss, float* dchat, cudaStream_t st) {
-  if (B <= 0) return IMP_OK;
+namespace {
+int check_modularity_args(int total_rows, int B, int max_len, int P1, int P2, float temp, const void* workspace) {
   if (P1 < 1 || P1 > 32 || P2 < 0 || P2 > 8) IMP_FAIL(IMP_ERR_ARG, "modularity: token groups (%d,%d) must be in [1,32] and [0,8]", P1, P2);
   if (total_rows <= 0 || max_len <= 0) IMP_FAIL(IMP_ERR_ARG, "modularity: empty input");
   if (!(temp > 0.f)) IMP_FAIL(IMP_ERR_ARG, "modularity: temp must be positive");
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) IMP_FAIL(IMP_ERR_ARG, "modularity: workspace must be 256-byte aligned");
+  (void)B;
+  return IMP_OK;
+}
+}  // namespace
+
+// sections of the workspace a multi-GPU caller exchanges between the two phases (byte offsets and sizes):
+//   0 xh (row-major, 512 B per row)   1 lfix (tiled, PtPad*256 B per 64-row tile)   2 colsum (B*256 floats)   3 negflag (1 int)
+void modularity_workspace_sections(int total_rows, int B, int P1, int P2, size_t* offsets, size_t* sizes) {
+  const int PtPad = 4 * (quads1(P1) + quads2(P2));
+  Carve c = carve(nullptr, total_rows, B, PtPad);
+  const uint8_t* base = nullptr;
+  const size_t ntile = ((size_t)total_rows + kBM + kBN + 63) / 64;
+  offsets[0] = reinterpret_cast<const uint8_t*>(c.xh) - base;      sizes[0] = (size_t)total_rows * kD * 2;
+  offsets[1] = reinterpret_cast<const uint8_t*>(c.lfix) - base;    sizes[1] = ntile * PtPad * 64 * 4;
+  offsets[2] = reinterpret_cast<const uint8_t*>(c.colsum) - base;  sizes[2] = (size_t)B * kD * 4;
+  offsets[3] = reinterpret_cast<const uint8_t*>(c.negflag) - base; sizes[3] = 4;
+}
+
+// Phase 1: zero the accumulators and run the prep kernel over the global rows [row_lo, row_lo + local_rows) whose
+// features are at h_local (a whole batch: row_lo = 0, local_rows = total_rows).
+int launch_modularity_prepare(const bf16* h_local, int local_rows, int row_lo, int total_rows, const int* cu, int B,
+                              const float* chat, int P1, int P2, void* workspace, cudaStream_t st) {
+  if (B <= 0) return IMP_OK;
+  int rc = check_modularity_args(total_rows, B, 1, P1, P2, 1.f, workspace);
+  if (rc) return rc;
+  if (row_lo < 0 || local_rows < 0 || row_lo + local_rows > total_rows || (row_lo & 63))
+    IMP_FAIL(IMP_ERR_ARG, "modularity: row window [%d,+%d) must lie in [0,%d) and start on a multiple of 64", row_lo, local_rows, total_rows);
   const int nq1 = quads1(P1), nq2 = quads2(P2);
-  const int P1pad = 4 * nq1, PtPad = 4 * (nq1 + nq2), Pt = P1 + P2;
+  const int P1pad = 4 * nq1, PtPad = 4 * (nq1 + nq2);
   Carve c = carve(workspace, total_rows, B, PtPad);
   // padding rows of xh are read by the tile loads of the last row block / column tile: keep them finite
   IMP_CUDA(cudaMemsetAsync(c.xh + (size_t)total_rows * kD, 0, (size_t)(kBM + kBN) * kD * 2, st));
   IMP_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(workspace) + c.zero_off, 0, c.zero_bytes, st));
-  IMP_CUDA(cudaMemsetAsync(dchat, 0, (size_t)B * Pt * kD * 4, st));
-
+  if (local_rows == 0) return IMP_OK;
   PrepParams pp;
-  pp.h = h; pp.cu = cu; pp.chat = chat; pp.xh = c.xh; pp.invn = c.invn; pp.lfix = c.lfix; pp.colsum = c.colsum;
+  pp.h = h_local; pp.cu = cu; pp.chat = chat; pp.xh = c.xh; pp.invn = c.invn; pp.lfix = c.lfix; pp.colsum = c.colsum;
   pp.negflag = c.negflag; pp.R = total_rows; pp.B = B; pp.P1 = P1; pp.P2 = P2; pp.P1pad = P1pad;
-  int rc;
+  pp.row_lo = row_lo; pp.row_hi = row_lo + local_rows;
   switch (PtPad) {
     case 8: rc = run_prep<8>(pp, st); break;
     case 16: rc = run_prep<16>(pp, st); break;
@@ -909,7 +939,23 @@ int launch_modularity(const bf16* h, int total_rows, const int* cu, int B, int m
     case 40: rc = run_prep<40>(pp, st); break;
     default: IMP_FAIL(IMP_ERR_ARG, "modularity: unsupported padded token count %d", PtPad);
   }
+  return rc;
+}
+
+// Phase 2: degrees over all rows, then the pair sweep and the finish kernel for the rows [row_lo, row_lo + local_rows)
+// against all columns.  For a window smaller than the batch, `loss` and `dchat` are this window's partial sums.
+int launch_modularity_execute(const bf16* h_local, int local_rows, int row_lo, int total_rows, const int* cu, int B,
+                              int max_len, int P1, int P2, float temp, void* workspace, float* loss, float* dchat,
+                              cudaStream_t st) {
+  if (B <= 0) return IMP_OK;
+  int rc = check_modularity_args(total_rows, B, max_len, P1, P2, temp, workspace);
   if (rc) return rc;
+  const int nq1 = quads1(P1), nq2 = quads2(P2);
+  const int P1pad = 4 * nq1, PtPad = 4 * (nq1 + nq2), Pt = P1 + P2;
+  Carve c = carve(workspace, total_rows, B, PtPad);
+  IMP_CUDA(cudaMemsetAsync(dchat, 0, (size_t)B * Pt * kD * 4, st));
+  const bool whole = (row_lo == 0 && local_rows == total_rows);
+  const int own_len = whole ? max_len : local_rows;          // longest run of owned rows inside one bag
 
   DegParams dp;
   dp.xh = c.xh; dp.cu = cu; dp.colsum = c.colsum; dp.negflag = c.negflag; dp.d = c.d; dp.e = c.e; dp.R = total_rows; dp.B = B;
@@ -921,26 +967,39 @@ int launch_modularity(const bf16* h, int total_rows, const int* cu, int B, int m
   if ((rc = imp_make_tmap_2d(&tb, c.xh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, rpad, kD * 2, 64, kBN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   GramParams gp;
   gp.cu = cu; gp.lfix = c.lfix; gp.d = c.d; gp.e = c.e; gp.T = c.T; gp.s = c.s; gp.negflag = c.negflag; gp.inv_temp = 1.f / temp;
-  const int row_blocks = (max_len + kBM - 1) / kBM;
-  const int col_tiles = (max_len + kBN - 1) / kBN + 1;        // absolute tiles: a bag may straddle one more
-  // enough CTAs for >= 2 waves; at least 16 column tiles per CTA to amortise the A block load
-  int nsplit = std::max(1, std::min((2 * imp_num_sms() + row_blocks * B - 1) / (row_blocks * B), std::max(1, col_tiles / 16)));
-  gp.tiles_per_split = (col_tiles + nsplit - 1) / nsplit;
-  nsplit = (col_tiles + gp.tiles_per_split - 1) / gp.tiles_per_split;
-  const dim3 grid(row_blocks, nsplit, B);
-  if ((rc = run_degrees(ta, tb, gp, grid, st))) return rc;     // exits at once unless some feature is negative
+  gp.row_lo = 0; gp.row_hi = INT_MAX;
+  {   // general (signed) degrees: every row of every bag, exits at once unless some feature is negative
+    const int row_blocks = (max_len + kBM - 1) / kBM;
+    const int col_tiles = (max_len + kBN - 1) / kBN;
+    int nsplit = std::max(1, std::min((2 * imp_num_sms() + row_blocks * B - 1) / (row_blocks * B), std::max(1, col_tiles / 16)));
+    gp.tiles_per_split = (col_tiles + nsplit - 1) / nsplit;
+    nsplit = (col_tiles + gp.tiles_per_split - 1) / gp.tiles_per_split;
+    if ((rc = run_degrees(ta, tb, gp, dim3(row_blocks, nsplit, B), st))) return rc;
+  }
+  if (local_rows > 0) {
+    gp.row_lo = whole ? 0 : row_lo; gp.row_hi = whole ? INT_MAX : row_lo + local_rows;
+    const int row_blocks = (own_len + kBM - 1) / kBM;
+    const int col_tiles = (max_len + kBN - 1) / kBN + 1;        // absolute tiles: a bag may straddle one more
+    // enough CTAs for >= 2 waves; at least 16 column tiles per CTA to amortise the A block load
+    int nsplit = std::max(1, std::min((2 * imp_num_sms() + row_blocks * B - 1) / (row_blocks * B), std::max(1, col_tiles / 16)));
+    gp.tiles_per_split = (col_tiles + nsplit - 1) / nsplit;
+    nsplit = (col_tiles + gp.tiles_per_split - 1) / gp.tiles_per_split;
+    const dim3 grid(row_blocks, nsplit, B);
 #define IMP_SWEEP(a, b2) rc = run_sweep<a, b2>(ta, tb, gp, grid, st)
-  if (nq2 == 0) { if (nq1 == 2) IMP_SWEEP(2, 0); else if (nq1 == 4) IMP_SWEEP(4, 0); else IMP_SWEEP(8, 0); }
-  else { if (nq1 == 2) IMP_SWEEP(2, 2); else if (nq1 == 4) IMP_SWEEP(4, 2); else IMP_SWEEP(8, 2); }
+    if (nq2 == 0) { if (nq1 == 2) IMP_SWEEP(2, 0); else if (nq1 == 4) IMP_SWEEP(4, 0); else IMP_SWEEP(8, 0); }
+    else { if (nq1 == 2) IMP_SWEEP(2, 2); else if (nq1 == 4) IMP_SWEEP(4, 2); else IMP_SWEEP(8, 2); }
 #undef IMP_SWEEP
-  if (rc) return rc;
+    if (rc) return rc;
+  }
 
   FinishParams fp;
-  fp.h = h; fp.invn = c.invn; fp.lfix = c.lfix; fp.T = c.T; fp.cu = cu; fp.s = c.s;
+  fp.h = h_local; fp.invn = c.invn; fp.lfix = c.lfix; fp.T = c.T; fp.cu = cu; fp.s = c.s;
   fp.dchat = dchat; fp.loss = loss; fp.P1 = P1; fp.P2 = P2; fp.P1pad = P1pad;
-  const int fin_chunks = std::max(1, std::min((max_len + 255) / 256, (4 * imp_num_sms() + B - 1) / B));
-  fp.rows_per_cta = ((max_len + fin_chunks - 1) / fin_chunks + 31) & ~31;
-  const dim3 fgrid((max_len + fp.rows_per_cta - 1) / fp.rows_per_cta, B);
+  fp.row_lo = whole ? 0 : row_lo; fp.row_hi = whole ? INT_MAX : row_lo + local_rows; fp.h_row0 = row_lo;
+  const int fin_len = std::max(own_len, 1);
+  const int fin_chunks = std::max(1, std::min((fin_len + 255) / 256, (4 * imp_num_sms() + B - 1) / B));
+  fp.rows_per_cta = ((fin_len + fin_chunks - 1) / fin_chunks + 31) & ~31;
+  const dim3 fgrid((fin_len + fp.rows_per_cta - 1) / fp.rows_per_cta, B);
   switch (PtPad) {
     case 8: IMP_LAUNCH("modularity_finish", st, modularity_finish_kernel<8><<<fgrid, 256, 0, st>>>(fp)); break;
     case 16: IMP_LAUNCH("modularity_finish", st, modularity_finish_kernel<16><<<fgrid, 256, 0, st>>>(fp)); break;
@@ -951,4 +1010,13 @@ int launch_modularity(const bf16* h, int total_rows, const int* cu, int B, int m
   }
   IMP_LAUNCH_CHECK();
   return IMP_OK;
+}
+
+int launch_modularity(const bf16* h, int total_rows, const int* cu, int B, int max_len, const float* chat, int P1, int P2,
+                      float temp, void* workspace, float* loss, float* dchat, cudaStream_t st) {
+  if (B <= 0) return IMP_OK;
+  int rc = check_modularity_args(total_rows, B, max_len, P1, P2, temp, workspace);
+  if (rc) return rc;
+  if ((rc = launch_modularity_prepare(h, total_rows, 0, total_rows, cu, B, chat, P1, P2, workspace, st))) return rc;
+  return launch_modularity_execute(h, total_rows, 0, total_rows, cu, B, max_len, P1, P2, temp, workspace, loss, dchat, st);
 }

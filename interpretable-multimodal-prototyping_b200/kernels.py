@@ -166,6 +166,53 @@ def modularity(h: torch.Tensor, cu_seqlens: torch.Tensor, max_len: int, chat: to
     return loss, dchat
 
 
+def modularity_sharded(h_local: torch.Tensor, row_offset: int, total_rows: int, chat: torch.Tensor, n_tok1: int,
+                       n_tok2: int, temp: float, group) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One bag of ``total_rows`` patches whose rows [row_offset, row_offset + h_local.shape[0]) live on this rank
+    (row_offset a multiple of 64; ranks in rank order cover [0,total_rows) without gaps).  Returns the GLOBAL
+    (loss (1,2), dchat (1,Pt,256)), identical on every rank of ``group``: prepare -> exchange of xh / fixed-point
+    assignments / column sums / sign flag -> sweep of the local rows -> sum of the partial results."""
+    import torch.distributed as dist
+    _chk(h_local, torch.bfloat16, "h_local"); _chk(chat, torch.float32, "chat")
+    dev = chat.device
+    local_rows = int(h_local.shape[0])
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nbytes = _lib.query("imp_modularity_workspace_bytes", total_rows, 1, n_tok1, n_tok2)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    cu = torch.tensor([0, total_rows], dtype=torch.int32, device=dev)
+    offs, sizes = (ctypes.c_size_t * 4)(), (ctypes.c_size_t * 4)()
+    _lib.call("imp_modularity_sections", total_rows, 1, n_tok1, n_tok2, offs, sizes)
+    _lib.call("imp_modularity_prepare", h_local, local_rows, int(row_offset), int(total_rows), cu, 1, chat, int(n_tok1),
+              int(n_tok2), ws, _lib.stream_ptr())
+    # who owns which rows
+    mine = torch.tensor([row_offset, local_rows], dtype=torch.int64, device=dev)
+    allw = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allw, mine, group=group)
+    windows = [tuple(int(v) for v in w.tolist()) for w in allw]
+    ntile_total = (total_rows + 128 + 64 + 63) // 64
+    tile_bytes = int(sizes[1]) // ntile_total
+    for r, (lo, n) in enumerate(windows):
+        if n == 0:
+            continue
+        src = dist.get_global_rank(group, r) if group is not None else r
+        xh = ws[int(offs[0]) + lo * 512: int(offs[0]) + (lo + n) * 512]
+        t0, t1 = lo // 64, (lo + n + 63) // 64
+        lf = ws[int(offs[1]) + t0 * tile_bytes: int(offs[1]) + t1 * tile_bytes]
+        dist.broadcast(xh, src=src, group=group)
+        dist.broadcast(lf, src=src, group=group)
+    colsum = ws[int(offs[2]): int(offs[2]) + int(sizes[2])].view(torch.float32)
+    flag = ws[int(offs[3]): int(offs[3]) + 4].view(torch.int32)
+    dist.all_reduce(colsum, group=group)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    loss = torch.empty(1, 2, device=dev, dtype=torch.float32)
+    dchat = torch.empty_like(chat)
+    _lib.call("imp_modularity_execute", h_local, local_rows, int(row_offset), int(total_rows), cu, 1, int(total_rows),
+              int(n_tok1), int(n_tok2), float(temp), ws, loss, dchat, _lib.stream_ptr())
+    packed = torch.cat([loss.reshape(-1), dchat.reshape(-1)])
+    dist.all_reduce(packed, group=group)
+    return packed[:2].view(1, 2), packed[2:].view_as(chat)
+
+
 def _int_array(vals):
     return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
 

@@ -36,6 +36,37 @@ class _ModularityFn(torch.autograd.Function):
         return None, None, None, dchat * g.unsqueeze(-1), None, None, None
 
 
+class _ShardedModularityFn(torch.autograd.Function):
+    """One bag sharded by rows over the ranks of ``group``; loss and token gradient are global on every rank."""
+
+    @staticmethod
+    def forward(ctx, h_local, row_offset, total_rows, chat, n1, n2, temp, group):
+        loss, dchat = kernels.modularity_sharded(h_local, row_offset, total_rows, chat.contiguous(), n1, n2, temp, group)
+        ctx.save_for_backward(dchat)
+        ctx.n1, ctx.n2 = n1, n2
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dchat,) = ctx.saved_tensors
+        g = torch.cat([dloss[:, 0:1].expand(-1, ctx.n1), dloss[:, 1:2].expand(-1, ctx.n2)], dim=1)
+        return None, None, None, dchat * g.unsqueeze(-1), None, None, None, None
+
+
+def modularity_terms_sharded(h_local: torch.Tensor, row_offset: int, total_rows: int, c_proto: torch.Tensor,
+                             c_omic: Optional[torch.Tensor] = None, temp: float = 0.1, group=None) -> torch.Tensor:
+    """Giant-bag mode: ONE bag of ``total_rows`` patches, this rank holding the rows
+    [row_offset, row_offset + len(h_local)) (``parallel.shard_bounds`` produces such windows); c_proto (1,P,256)
+    and c_omic (1,Q,256) replicated.  -> (1,2) global modularity terms, same on every rank."""
+    n1 = c_proto.shape[1]
+    chat = normalize_tokens(c_proto.float())
+    n2 = 0
+    if c_omic is not None:
+        n2 = c_omic.shape[1]
+        chat = torch.cat([chat, normalize_tokens(c_omic.float())], dim=1)
+    return _ShardedModularityFn.apply(h_local.detach(), int(row_offset), int(total_rows), chat, n1, n2, float(temp), group)
+
+
 def modularity_terms(h: torch.Tensor, cu_seqlens: torch.Tensor, max_len: int, c_proto: torch.Tensor,
                      c_omic: Optional[torch.Tensor] = None, temp: float = 0.1) -> torch.Tensor:
     """h (R,256) bf16 packed (no gradient), c_proto (B,P,256), c_omic (B,Q,256) or None ->

@@ -1,6 +1,8 @@
 """2 GPUs, NCCL: (a) a bag sharded over ranks (LSE merge of the partial softmax states, all-reduced
 dq~/dW1) reproduces the single-GPU tokens and gradients; (b) slide-parallel gradient all-reduce equals
-the single-GPU gradients over all slides.  Skipped with fewer than 2 GPUs."""
+the single-GPU gradients over all slides; (c) the modularity loss of one bag sharded by rows over the ranks
+(all-gather of xh / assignments, all-reduce of the partial traces and token gradients) equals the single-GPU
+loss and gradients.  Skipped with fewer than 2 GPUs."""
 import os
 import sys
 
@@ -66,7 +68,24 @@ def _worker(rank, world, port, q):
         S.allreduce_gradients(lv, world)
         full = run_slides(list(range(len(lens))))
         err_dp = max(rel(lv[k].grad * world, full[k].grad) for k in full.keys())
-        q.put((rank, err_c, err_g, err_dp))
+
+        # modularity of one bag sharded by rows (imp_modularity_prepare / _execute around the collectives)
+        from imp_b200 import modularity as MOD
+        nmod = 3000 + 37
+        gm = torch.Generator().manual_seed(9)
+        hm = torch.relu(torch.randn(nmod, 256, generator=gm) + 0.5 * torch.randn(1, 256, generator=gm)).bfloat16().to(dev)
+        cp = torch.randn(1, 16, 256, generator=gm).to(dev)
+        co = torch.randn(1, 7, 256, generator=gm).to(dev)
+        cp_s, co_s = cp.clone().requires_grad_(True), co.clone().requires_grad_(True)
+        a2, b2 = P.shard_bounds(nmod, world)[rank]
+        t_sh = MOD.modularity_terms_sharded(hm[a2:b2].contiguous(), a2, nmod, cp_s, co_s, group=dist.group.WORLD)
+        (t_sh[0, 0] + 2.0 * t_sh[0, 1]).backward()
+        cp_f, co_f = cp.clone().requires_grad_(True), co.clone().requires_grad_(True)
+        cu_m = torch.tensor([0, nmod], dtype=torch.int32, device=dev)
+        t_full = MOD.modularity_terms(hm, cu_m, nmod, cp_f, co_f)
+        (t_full[0, 0] + 2.0 * t_full[0, 1]).backward()
+        err_m = max(((t_sh - t_full).abs() / (t_full.abs() + 1e-6)).max().item(), rel(cp_s.grad, cp_f.grad), rel(co_s.grad, co_f.grad))
+        q.put((rank, err_c, err_g, err_dp, err_m))
     finally:
         dist.destroy_process_group()
 
@@ -85,7 +104,8 @@ def test_two_gpu_sharded_bag_and_slide_parallel():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, err_c, err_g, err_dp in res:
+    for rank, err_c, err_g, err_dp, err_m in res:
         assert err_c < 2e-4, (rank, err_c)          # same kernels, different split of the softmax
         assert err_g < 2e-3, (rank, err_g)
         assert err_dp < 2e-3, (rank, err_dp)
+        assert err_m < 5e-4, (rank, err_m)          # same kernels, row blocks split over the ranks
