@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="report the eager (Python-launched) steps instead of CUDA-graph replays")
+    ap.add_argument("--missing-omics", type=float, default=0.0,
+                    help="configs[2]: fraction of slides whose genomics are missing (gene values imputed by the cohort means "
+                         "in the encoder gather, umeml_gan.py:391-392); 0 = fully paired batches (configs[1])")
     ap.add_argument("--workload", default="fusion", choices=["fusion", "kmeans"],
                     help="fusion: the headline (configs[1]); kmeans: configs[4], 2^20 x 512 fp32 -> 32 centroids, one assignment pass per step")
     return ap.parse_args()
@@ -193,6 +196,10 @@ def run_ours(args):
     cot_p = torch.randn(B, P, 256, device=dev, generator=gen) * 1e-2
     cot_o = torch.randn(B, N_PATHWAYS + 1, 256, device=dev, generator=gen) * 1e-2
     batch = {"x_packed": x, "cu_seqlens": cu, "max_len": N, "omic": omic}
+    if args.missing_omics > 0:      # incompletely paired batch: whole-sample masks, imputed inside the encoder kernel
+        miss = (torch.rand(B, device=dev, generator=gen) < args.missing_omics)
+        batch["insample_without_omic"] = miss[:, None].expand(B, sum(GROUP_SIZES)).to(torch.int32).contiguous()
+        net.omic_means = torch.full((sum(GROUP_SIZES),), 0.5, device=dev)
     params = [p for p in runner.parameters()]
 
     def one_step(b, cp, co, with_mod=True, lengths=None):
@@ -399,7 +406,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "bags_per_step_per_gpu": B, "patches": N, "prototypes": P, "pathways": N_PATHWAYS,
-                       "modularity": True, "dropout": 0.25,
+                       "modularity": True, "dropout": 0.25, "missing_omics_fraction": args.missing_omics,
                        "l2": "inputs larger than L2: %.0f MiB of bf16 features per step per GPU" % (B * N * D_IN * 2 / 2 ** 20),
                        "parallelism": "dp%d" % world},
             "streaming_only": {"value": value_s, "unit": "bags/s", "ms_per_step": ms_s / args.steps,

@@ -25,7 +25,8 @@ def _check(x, mu, assign):
     return (a == ref).float().mean().item()
 
 
-@pytest.mark.parametrize("n,k,d", [(1, 1, 512), (255, 6, 512), (4096, 32, 512), (65536 + 19, 32, 512), (3000, 16, 256)])
+@pytest.mark.parametrize("n,k,d", [(1, 1, 512), (255, 6, 512), (4096, 32, 512), (65536 + 19, 32, 512), (3000, 16, 256),
+                                   (5000, 48, 512), (2500, 64, 256), (3333, 32, 1024), (777, 3, 32)])   # every (K, rows-per-thread) variant
 def test_kmeans_assign_vs_oracle(n, k, d):
     from imp_b200 import kernels
     g = torch.Generator().manual_seed(n)
