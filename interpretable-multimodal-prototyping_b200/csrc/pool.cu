@@ -9,10 +9,11 @@
 //   dq~_p = sum_n dS_pn h_n
 //   dh_n  = sum_blocks sum_p (a_pn dpooled_p + dS_pn q~_p) ,  dz = dh * keep_scale * [h > 0]
 //
-// Streaming kernels over h (R,256) bf16: one TMA producer warp fills a ring of 64-row tiles
-// (128-byte swizzle), eight consumer warps run the P-wide contractions with warp-level
-// mma.sync (K = P is far too small for a tcgen05 tile) and fp32 online-softmax statistics.
-// A bag is split over `nsplit` CTAs; partial states are merged by a log-sum-exp kernel.
+// Forward and dq~: streaming kernels over h (R,256) bf16: one TMA producer warp fills a ring of 64-row tiles
+// (128-byte swizzle), eight consumer warps run the P-wide contractions with warp-level mma.sync (the outputs
+// are P x 256 accumulators over the patch rows) and fp32 online-softmax statistics.  A bag is split over
+// `nsplit` CTAs; partial states are merged by a log-sum-exp kernel.
+// dz (the gradient that flows back into path_net) is a pair of dense GEMMs per tile and runs on tcgen05.
 #include "common.cuh"
 #include "launchers.h"
 
@@ -300,15 +301,11 @@ struct PoolBwdParams {
   const float* lse[2];     // (B,P)
   const float* delta[2];   // (B,P)
   float* part_dq;          // (B, nsplit, PP, 256): dq~ of block `dq_block`
-  float* part_db;          // (B*nsplit, 256) or null
-  bf16* dz;                // (R,256) or null
   int P, nsplit, tiles_per_split, dq_block;
-  int relu_mask;           // 1: dz = keep_scale*[h>0]*dh (path_net pre-activation); 0: dz = dh
-  float keep_scale;
 };
 
-template <int PP, int NB, bool DZ, int STAGES>
-__global__ void __launch_bounds__(kThreads, (!DZ && NB == 1 && PP <= 32) ? 2 : 1)
+template <int PP, int NB, int STAGES>
+__global__ void __launch_bounds__(kThreads, (NB == 1 && PP <= 32) ? 2 : 1)
 pool_bwd_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolBwdParams p) {
   constexpr int NCOL = 2 * NB * PP;           // stacked rows of G = columns of E
   constexpr int NGW = NB * PP / 16;           // prototype groups (8 wide) per warp
@@ -333,8 +330,6 @@ pool_bwd_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolBwdParams p)
   float* out_dq = p.part_dq + ((size_t)b * p.nsplit + split) * PP * kD;
   if (ntiles == 0) {
     for (int i = threadIdx.x; i < PP * kD; i += kThreads) out_dq[i] = 0.f;
-    if (DZ && p.part_db)
-      for (int i = threadIdx.x; i < kD; i += kThreads) p.part_db[((size_t)b * p.nsplit + split) * kD + i] = 0.f;
     return;
   }
   if (warp == kCW && lane == 0) {
@@ -386,9 +381,6 @@ pool_bwd_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolBwdParams p)
   for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
     for (int n = 0; n < 4; ++n) dq[mi][n][0] = dq[mi][n][1] = dq[mi][n][2] = dq[mi][n][3] = 0.f;
-  float dbacc[DZ ? 16 : 1][2];
-#pragma unroll
-  for (int n = 0; n < (DZ ? 16 : 1); ++n) dbacc[n][0] = dbacc[n][1] = 0.f;
 
   for (int i = 0; i < ntiles; ++i) {
     const int stage = i % STAGES;
@@ -401,7 +393,7 @@ pool_bwd_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolBwdParams p)
       score_tile<2 * NGW>(s, tile_base, g_base, mt, nrow0, lane);
       const int r_lo = tile_row0 + mt * 16 + g;
       const bool ok_lo = r_lo < row_end, ok_hi = (r_lo + 8) < row_end;
-      if (!DZ) bar_sync(1, kCW * 32);          // everyone is done reading E of the previous tile
+      bar_sync(1, kCW * 32);                   // everyone is done reading E of the previous tile
 #pragma unroll
       for (int j = 0; j < NGW; ++j) {
         const int gi = ch * NGW + j;
@@ -428,57 +420,6 @@ pool_bwd_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolBwdParams p)
     bar_sync(1, kCW * 32);
     // dq~ of the requested block: dS^T . h
     weighted_sum_tile<MT>(dq, tile_base, e_base, E_STRIDE, p.dq_block * 2 * PP, fb, lane);
-    if constexpr (DZ) {
-      bar_sync(1, kCW * 32);                   // all reads of h as an MMA operand are done
-      // dh = E . G for rows of m-tile mt, feature half ch, in two passes of 64 features
-#pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        float dh[8][4];
-#pragma unroll
-        for (int n = 0; n < 8; ++n) dh[n][0] = dh[n][1] = dh[n][2] = dh[n][3] = 0.f;
-        const int f0 = ch * 128 + pass * 64;
-        const int arow = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-#pragma unroll 2
-        for (int ks = 0; ks < NCOL / 16; ++ks) {
-          uint32_t a[4];
-          ldsm_x4(a, e_base + arow * E_STRIDE + (ks * 16 + (lane >> 4) * 8) * 2);
-          const int krow = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-#pragma unroll
-          for (int pr = 0; pr < 4; ++pr) {
-            uint32_t bq[4];
-            ldsm_x4_t(bq, g_base + gmat_off(krow, f0 + pr * 16 + (lane >> 4) * 8));
-            uint32_t b0[2] = {bq[0], bq[1]}, b1[2] = {bq[2], bq[3]};
-            mma_bf16_16816(dh[2 * pr], a, b0);
-            mma_bf16_16816(dh[2 * pr + 1], a, b1);
-          }
-        }
-        // relu/dropout mask from the stored activations; overwrite h with dz in place
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-          const int col = f0 + n * 8 + 2 * t;
-          uint32_t* p_lo = reinterpret_cast<uint32_t*>(tile_ptr + htile_off(mt * 16 + g, col));
-          uint32_t* p_hi = reinterpret_cast<uint32_t*>(tile_ptr + htile_off(mt * 16 + g + 8, col));
-          const uint32_t h_lo = *p_lo, h_hi = *p_hi;
-          const bool nm = p.relu_mask == 0;
-          const float z0 = (nm || bf16lo(h_lo) > 0.f) ? dh[n][0] * p.keep_scale : 0.f;
-          const float z1 = (nm || bf16hi(h_lo) > 0.f) ? dh[n][1] * p.keep_scale : 0.f;
-          const float z2 = (nm || bf16lo(h_hi) > 0.f) ? dh[n][2] * p.keep_scale : 0.f;
-          const float z3 = (nm || bf16hi(h_hi) > 0.f) ? dh[n][3] * p.keep_scale : 0.f;
-          *p_lo = pack_bf16x2(z0, z1);
-          *p_hi = pack_bf16x2(z2, z3);
-          dbacc[pass * 8 + n][0] += z0 + z2;    // masked rows contribute 0 (a = dS = 0 => dh = 0)
-          dbacc[pass * 8 + n][1] += z1 + z3;
-        }
-      }
-      bar_sync(1, kCW * 32);
-      // coalesced store of the valid rows of the dz tile
-      const int nvalid = min(kTM, row_end - tile_row0);
-      for (int it = threadIdx.x; it < nvalid * 32; it += kCW * 32) {
-        const int r = it >> 5, c = (it & 31) << 3;
-        const uint4 v = *reinterpret_cast<const uint4*>(tile_ptr + htile_off(r, c));
-        *reinterpret_cast<uint4*>(p.dz + (size_t)(tile_row0 + r) * kD + c) = v;
-      }
-    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);
   }
@@ -491,23 +432,6 @@ pool_bwd_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolBwdParams p)
       *reinterpret_cast<float2*>(out_dq + (size_t)(mi * 16 + g) * kD + col) = make_float2(dq[mi][n][0], dq[mi][n][1]);
       *reinterpret_cast<float2*>(out_dq + (size_t)(mi * 16 + g + 8) * kD + col) = make_float2(dq[mi][n][2], dq[mi][n][3]);
     }
-  if constexpr (DZ) if (p.part_db) {
-    bar_sync(1, kCW * 32);
-    float* s_db = reinterpret_cast<float*>(s_e);       // [4][256], E is no longer needed
-#pragma unroll
-    for (int n = 0; n < 16; ++n)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float v = dbacc[n][e];
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (g == 0) s_db[mt * kD + ch * 128 + (n >> 3) * 64 + (n & 7) * 8 + 2 * t + e] = v;
-      }
-    bar_sync(1, kCW * 32);
-    const int f = threadIdx.x;     // 256 consumer threads
-    p.part_db[((size_t)b * p.nsplit + split) * kD + f] = s_db[f] + s_db[kD + f] + s_db[2 * kD + f] + s_db[3 * kD + f];
-  }
 }
 
 // out[b][pi][f] = sum_s part[b][s][pi][f]   (pi < P <= PP); grid (P, B), 256 threads
@@ -799,16 +723,16 @@ int run_fwd(const CUtensorMap& tm, const PoolFwdParams& p, int B, cudaStream_t s
   IMP_LAUNCH("pool_fwd", st, pool_fwd_kernel<PP, STAGES><<<dim3(p.nsplit, B), kThreads, smem, st>>>(tm, p));
   return IMP_OK;
 }
-template <int PP, int NB, bool DZ, int STAGES>
+template <int PP, int NB, int STAGES>
 int run_bwd(const CUtensorMap& tm, const PoolBwdParams& p, int B, cudaStream_t st) {
   constexpr size_t smem = bwd_smem<PP, NB, STAGES>();
   static_assert(smem <= 227 * 1024, "pool_bwd shared memory");
   static bool done = false;
   if (!done) {
-    IMP_CUDA(cudaFuncSetAttribute(pool_bwd_kernel<PP, NB, DZ, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IMP_CUDA(cudaFuncSetAttribute(pool_bwd_kernel<PP, NB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done = true;
   }
-  IMP_LAUNCH(DZ ? "pool_bwd_dz" : "pool_bwd_dq", st, pool_bwd_kernel<PP, NB, DZ, STAGES><<<dim3(p.nsplit, B), kThreads, smem, st>>>(tm, p));
+  IMP_LAUNCH("pool_bwd_dq", st, pool_bwd_kernel<PP, NB, STAGES><<<dim3(p.nsplit, B), kThreads, smem, st>>>(tm, p));
   return IMP_OK;
 }
 
@@ -890,7 +814,7 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
   const int PP = pad_protos(P);
   PoolBwdParams p;
   split_plan(max_len, B, &p.nsplit, &p.tiles_per_split);
-  p.cu = cu; p.P = P; p.dq_block = dq_block; p.keep_scale = relu_mask ? keep_scale : 1.f; p.relu_mask = relu_mask;
+  p.cu = cu; p.P = P; p.dq_block = dq_block;
   for (int k = 0; k < 2; ++k) {
     const int s = k < nblocks ? k : 0;
     p.qt[k] = qt[s]; p.qt_stride[k] = qt_stride[s];
@@ -898,8 +822,7 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
     p.lse[k] = lse[s]; p.delta[k] = delta[s];
   }
   p.part_dq = workspace;
-  p.part_db = nullptr;
-  p.dz = nullptr;
+  float* part_db = nullptr;
   CUtensorMap tm;
   int rc = imp_make_tmap_2d(&tm, h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, total_rows, kD * 2, 64, kTM,
                             CU_TENSOR_MAP_SWIZZLE_128B);
@@ -910,7 +833,7 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
     q1.qt[0] = qt[dq_block]; q1.qt_stride[0] = qt_stride[dq_block];
     q1.dpool[0] = dpool[dq_block]; q1.lse[0] = lse[dq_block]; q1.delta[0] = delta[dq_block];
     q1.dq_block = 0;
-#define IMP_BWD(PPv, STv) rc = run_bwd<PPv, 1, false, STv>(tm, q1, B, st)
+#define IMP_BWD(PPv, STv) rc = run_bwd<PPv, 1, STv>(tm, q1, B, st)
     if (PP == 16) IMP_BWD(16, 2); else if (PP == 32) IMP_BWD(32, 2); else IMP_BWD(64, 3);
 #undef IMP_BWD
     if (rc) return rc;
@@ -934,11 +857,11 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
     else if (PP == 32) rc = nblocks == 1 ? run_dz<32, 1>(tmz, z, B, st) : run_dz<32, 2>(tmz, z, B, st);
     else rc = run_dz<64, 1>(tmz, z, B, st);
     if (rc) return rc;
-    p.part_db = z.part_db;
+    part_db = z.part_db;
   }
   IMP_LAUNCH("reduce_dq", st, reduce_dq_kernel<<<dim3(P, B), kD, 0, st>>>(p.part_dq, dq, P, PP, p.nsplit));
-  if (p.part_db) {
-    IMP_LAUNCH("reduce_db", st, reduce_db_kernel<<<1, kD, 0, st>>>(p.part_db, db1, B * nz, db_accumulate));
+  if (part_db) {
+    IMP_LAUNCH("reduce_db", st, reduce_db_kernel<<<1, kD, 0, st>>>(part_db, db1, B * nz, db_accumulate));
   }
   return IMP_OK;
 }
