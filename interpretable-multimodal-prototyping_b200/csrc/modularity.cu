@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(256) modularity_prep_kernel(const PrepParams p
   const int r0 = p.row_lo + blockIdx.x * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // ---------------- phase A ----------------
+  const int data_end0 = __ldg(p.cu + p.B);             // rows past cu[B] belong to no bag
   bool neg = false;
 #pragma unroll
   for (int rr = 0; rr < 8; ++rr) {
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(256) modularity_prep_kernel(const PrepParams p
     }
     float ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { ss += v[k] * v[k]; neg |= v[k] < 0.f; }
+    for (int k = 0; k < 8; ++k) { ss += v[k] * v[k]; neg |= (v[k] < 0.f) && (row < data_end0); }
     ss = warp_sum(ss);
     const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);          // F.normalize eps (utils.py:179,193)
 #pragma unroll
@@ -229,11 +230,13 @@ __global__ void __launch_bounds__(256) modularity_prep_kernel(const PrepParams p
       }
     }
   }
-  // rows of the tile past the end of the data keep the sweep's loads finite
-  if (p.row_hi == p.R && r0 + 64 > p.R) {
+  // rows of the tile that belong to no bag (past cu[B]: tile padding, or the unused tail of a buffer sized for the
+  // worst case) are masked in the sweep, but its loads must stay finite: 0 * NaN would poison the sums
+  const int data_end = __ldg(p.cu + p.B);
+  if (r0 + 64 > data_end) {
     for (int i = threadIdx.x; i < PTPAD * 64; i += 256) {
       const int slot = i >> 6, rl = i & 63;
-      if (r0 + rl >= p.R) p.lfix[lfix_index(r0 + rl, slot, PTPAD)] = (float)(kNMax * 32);
+      if (r0 + rl >= data_end) p.lfix[lfix_index(r0 + rl, slot, PTPAD)] = (float)(kNMax * 32);
     }
   }
 }
@@ -257,12 +260,13 @@ __global__ void __launch_bounds__(256) modularity_degrees_closed_kernel(const De
   __shared__ int s_bag[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * 64 + warp * 8;
+  const int data_end = __ldg(p.cu + p.B);
   int cur = -1;
   float acc = 0.f;
   float s[8];
   for (int rr = 0; rr < 8; ++rr) {
     const int row = r0 + rr;
-    if (row >= p.R) break;
+    if (row >= p.R || row >= data_end) break;          // rows past cu[B] belong to no bag
     int b = cur;
     if (cur < 0 || row >= __ldg(p.cu + cur + 1)) b = find_segment(p.cu, p.B, row);
     if (b != cur) {

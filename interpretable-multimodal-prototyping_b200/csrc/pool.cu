@@ -687,6 +687,14 @@ pool_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const DzParams p) {
   }
 }
 
+// dz rows past cu[B] belong to no bag (a packed buffer sized for the worst case): the dz kernel never visits them,
+// but dW1 = dz^T x sums over every row of the buffer, so they must be zero rather than whatever the allocator left
+__global__ void zero_tail_rows_kernel(bf16* __restrict__ dz, const int* __restrict__ cu, int B, int total_rows) {
+  const size_t begin = (size_t)__ldg(cu + B) * (kD / 8), end = (size_t)total_rows * (kD / 8);      // in uint4 units
+  for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (size_t)gridDim.x * blockDim.x)
+    reinterpret_cast<uint4*>(dz)[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 int pad_protos(int P) { return P <= 16 ? 16 : (P <= 32 ? 32 : 64); }
 
 template <int PP, int STAGES>
@@ -858,6 +866,7 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
     else rc = run_dz<64, 1>(tmz, z, B, st);
     if (rc) return rc;
     part_db = z.part_db;
+    IMP_LAUNCH("zero_tail_rows", st, zero_tail_rows_kernel<<<imp_num_sms(), 256, 0, st>>>(dz, cu, B, total_rows));
   }
   IMP_LAUNCH("reduce_dq", st, reduce_dq_kernel<<<dim3(P, B), kD, 0, st>>>(p.part_dq, dq, P, PP, p.nsplit));
   if (part_db) {

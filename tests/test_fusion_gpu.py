@@ -75,3 +75,40 @@ def test_strip_and_pack_exact():
     assert torch.equal(x[:ref.shape[0]].cpu(), ref)
     x3, cu3, ml3 = ops.strip_and_pack(img.cuda(), lengths=want)
     assert torch.equal(x3.cpu(), ref) and ml3 == 10000 and torch.equal(cu3, cu2)
+
+
+def test_reference_batch_layout_without_host_lengths_matches_packed_bags():
+    """The reference batch layout (B,Npad,512) with -10000 row padding, lengths found on the device (no host
+    sync): the packed buffer is sized for the worst case, so rows past cu[B] belong to no bag.  Tokens and every
+    gradient must equal the run on exactly packed bags, also when the allocator hands out dirty memory."""
+    from imp_b200 import ops
+    from oracle import imp_oracle as O
+    dev = "cuda"
+    params = make_params(0)
+    lens, npad, P = [300, 200, 417], 512, 16
+    bags = [b.bfloat16().float() for b in make_bags(lens, 4)]
+    img = torch.full((len(lens), npad, 512), O.SENTINEL)
+    for i, b in enumerate(bags):
+        img[i, :b.shape[0]] = b
+    g = torch.Generator().manual_seed(2)
+    p_proto = (torch.rand(1, P, 256, generator=g) * 2 - 1) / P
+    cot = torch.randn(len(lens), P, 256, generator=g)
+
+    def run(x, cu, max_len):
+        leaves = {k: v.clone().to(dev).requires_grad_(True) for k, v in params.items()}
+        c, _ = ops.proto_fusion(x, cu, max_len, p_proto.to(dev), leaves["path_net.0.weight"], leaves["path_net.0.bias"],
+                                [block_tensors(leaves, 0), block_tensors(leaves, 1)])
+        (c * cot.to(dev)).sum().backward()
+        return c.detach(), {k: v.grad for k, v in leaves.items()}
+
+    x_ref = torch.cat(bags).to(dev).bfloat16().contiguous()
+    c_ref, g_ref = run(x_ref, ops._cu_from_lengths(lens, dev), max(lens))
+    poison = torch.full((64 << 20,), float("nan"), device=dev)      # dirty the allocator's free blocks
+    del poison
+    x, cu, max_len = ops.strip_and_pack(img.to(dev))                   # lengths from the device sentinel scan
+    assert x.shape[0] == len(lens) * npad and cu.tolist() == [0, 300, 500, 917]
+    c, gr = run(x, cu, max_len)
+    assert rel(c, c_ref) < 1e-5
+    for k in g_ref:
+        assert torch.isfinite(gr[k]).all(), k
+        assert rel(gr[k], g_ref[k]) < 1e-4, (k, rel(gr[k], g_ref[k]))

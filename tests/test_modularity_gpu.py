@@ -59,6 +59,30 @@ def test_modularity_batched_varlen_matches_single():
         assert abs(batched[i, 0].item() - single.item()) <= 1e-4 * abs(single.item()) + 1e-6
 
 
+@pytest.mark.parametrize("tail_kind", ["nonneg", "signed"])
+def test_rows_past_the_last_bag_and_dirty_workspace_are_ignored(tail_kind):
+    """strip_and_pack without host lengths returns a buffer sized for the worst case: rows past cu[B] belong to no
+    bag (there h = relu(b1), a constant non-negative row).  They must enter neither the degrees of the last bag nor
+    the sign flag, and whatever the caching allocator left in the workspace must not leak into the sums."""
+    from imp_b200 import modularity as M
+    lens = [300, 200]
+    hs, cs = [], []
+    for i, n in enumerate(lens):
+        h, c1, _ = _inputs(n, 6, 0, 70 + i)
+        hs.append(h); cs.append(c1)
+    tail = torch.randn(524, 256)
+    tail = (tail.abs() if tail_kind == "nonneg" else tail).bfloat16()         # rows owned by no bag
+    hcat = torch.cat(hs + [tail]).cuda()
+    cu = torch.tensor([0, 300, 500], dtype=torch.int32, device="cuda")
+    poison = torch.full((64 << 20,), float("nan"), device="cuda")             # dirty the allocator's free blocks
+    del poison
+    batched = M.modularity_terms(hcat, cu, 512, torch.stack(cs).cuda())
+    assert torch.isfinite(batched).all()
+    for i, n in enumerate(lens):
+        single = M.compute_modularity(cs[i].cuda().unsqueeze(0), hs[i].cuda().float().unsqueeze(0))
+        assert abs(batched[i, 0].item() - single.item()) <= 1e-4 * abs(single.item()) + 1e-6
+
+
 def test_signed_features_use_the_gram_degrees():
     """compute_modularity accepts any x (utils.py:205-228).  Behind path_net's ReLU the features are >= 0 and the
     degrees come from the closed form d_i = xh_i.(sum_j xh_j) - |xh_i|^2; signed features must take the Gram sweep
