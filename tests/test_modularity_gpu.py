@@ -59,6 +59,28 @@ def test_modularity_batched_varlen_matches_single():
         assert abs(batched[i, 0].item() - single.item()) <= 1e-4 * abs(single.item()) + 1e-6
 
 
+def test_empty_bag_inside_a_batch():
+    """An incompletely filled batch: a bag without patches between two real ones yields loss 0 and leaves the
+    neighbours untouched (pooling defines pooled = 0, lse = -inf for it)."""
+    from imp_b200 import kernels, modularity as M
+    lens = [130, 0, 257]
+    hs, cs = [], []
+    for i, n in enumerate(lens):
+        h, c1, _ = _inputs(max(n, 1), 16, 0, 90 + i)
+        hs.append(h[:n]); cs.append(c1)
+    hcat = torch.cat(hs).cuda()
+    cu = torch.tensor([0, 130, 130, 387], dtype=torch.int32, device="cuda")
+    c = torch.stack(cs).cuda().requires_grad_(True)
+    batched = M.modularity_terms(hcat, cu, 257, c)
+    batched[:, 0].sum().backward()
+    assert batched[1, 0].item() == 0.0 and torch.isfinite(c.grad).all() and c.grad[1].abs().max().item() == 0.0
+    for i in (0, 2):
+        single = M.compute_modularity(cs[i].cuda().unsqueeze(0), hs[i].cuda().float().unsqueeze(0))
+        assert abs(batched[i, 0].item() - single.item()) <= 1e-4 * abs(single.item()) + 1e-6
+    pooled, lse = kernels.pool_fwd(hcat, cu, 257, torch.randn(1, 16, 256, device="cuda") * 0.05)
+    assert pooled[1].abs().max().item() == 0.0 and torch.isinf(lse[1]).all() and torch.isfinite(pooled[[0, 2]]).all()
+
+
 @pytest.mark.parametrize("tail_kind", ["nonneg", "signed"])
 def test_rows_past_the_last_bag_and_dirty_workspace_are_ignored(tail_kind):
     """strip_and_pack without host lengths returns a buffer sized for the worst case: rows past cu[B] belong to no
