@@ -18,7 +18,7 @@
 //   sweep           : the trace and T_ip = sum_j 2 g_ij (1-delta^2)/temp u_ij [p = argmax]; Gram tiles on tcgen05,
 //                     the (max,x) contraction over tokens in the log domain as a (min,+) contraction of
 //                     integer-valued floats: FADD2 + FMNMX3 per token pair, arg-min in the low mantissa bits
-//   finish          : dC = T / C, dchat_p = sum_i dC_ip xh_i, loss per token group
+//   finish          : dC = T / C, dchat_p = sum_i dC_ip xh_i as a tcgen05 GEMM (A = dC / |x| split hi + lo, B = h), loss per group
 // Up to two token groups (<= 32 and <= 8 tokens) share A, d and e (the reference evaluates the
 // prototype tokens and the omic tokens against the same bag, umeml_gan.py:520-521).
 #include "common.cuh"
@@ -742,7 +742,6 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
 
 // ------------------------------------------------------------------------------------------
 // finish: dC = T / C (C = exp2(kCOff - N/2^kLogShift)), dchat_p = sum_i dC_ip xh_i ; loss per group
-//   grid (row chunks, B), 256 threads = features; dchat accumulated with atomicAdd
 // ------------------------------------------------------------------------------------------
 struct FinishParams {
   const bf16* h;
@@ -753,70 +752,177 @@ struct FinishParams {
   const double* s;
   float* dchat;       // (B, Pt, 256), zeroed by the launcher
   float* loss;        // (B, 2)
-  int P1, P2, P1pad, rows_per_cta;
+  int P1, P2, P1pad, rows_per_cta;    // rows_per_cta: 64-row tiles per CTA
   int row_lo, row_hi;       // rows owned by this call; h points at global row h_row0
   int h_row0;
 };
 
+// ------------------------------------------------------------------------------------------
+// finish on tcgen05:  dchat[slot][f] = sum_rows (dC[row][slot] / |x_row|) * h[row][f]   (a PtPad x N x 256 GEMM per bag)
+//   per absolute 64-row tile: TMA box of h (exact in bf16: the MN-major B operand), bulk copies of the T and L tiles
+//   (token-major); four builder warps turn them into a = T / C / |x| split into two bf16 MN-major A operands
+//   [64 rows][64 slots] (a = hi + lo keeps ~16 mantissa bits), one thread issues 2 x 4 MMAs 128 x 256 x 16 into a TMEM
+//   accumulator that lives for the whole CTA (rows 64..127 of A are a zero box); at the end the builder warps read
+//   the PtPad real lanes and add them to dchat.
+// ------------------------------------------------------------------------------------------
+constexpr int kFtStages = 3;
+constexpr int kFtThreads = 6 * 32;
 template <int PTPAD>
-__global__ void __launch_bounds__(256) modularity_finish_kernel(const FinishParams p) {
-  __shared__ __align__(16) float s_dc[32][PTPAD];
-  const int b = blockIdx.y, f = threadIdx.x;
+constexpr size_t finish_tc_smem() { return 1024 + (size_t)kFtStages * (kBBytes + 2 * PTPAD * 256 + 16384) + 8192 + 256; }
+
+template <int PTPAD>
+__global__ void __launch_bounds__(kFtThreads, 1)
+modularity_finish_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const FinishParams p) {
+  constexpr int kTL = PTPAD * 256;                       // bytes of one T (or L) tile: [PTPAD][64] fp32
+  constexpr int kStage = kBBytes + 2 * kTL + 16384;      // h box | T tile | L tile | A hi box | A lo box
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* s_zero = smem + kFtStages * kStage;           // second 64-wide M box of A: zeros
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_zero + 8192);
+  uint64_t* full = bars;                  // [3] loads -> builders + MMA
+  uint64_t* afull = bars + kFtStages;     // [3] 4 builder warps -> MMA
+  uint64_t* empty = afull + kFtStages;    // [3] MMA commit -> producer
+  uint64_t* tfull = empty + kFtStages;    // all MMAs retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int b = blockIdx.y;
   const int row_begin = __ldg(p.cu + b), row_end = __ldg(p.cu + b + 1);
   const int Pt = p.P1 + p.P2;
-  if (blockIdx.x == 0 && f < 2) {
-    p.loss[b * 2 + f] = (float)(-100.0 * p.s[(size_t)b * 2 + f]);          // utils.py:222-228: -100 tr((W/e) delta)
+  if (blockIdx.x == 0 && threadIdx.x < 2)
+    p.loss[b * 2 + threadIdx.x] = (float)(-100.0 * p.s[(size_t)b * 2 + threadIdx.x]);     // utils.py:222-228
+  const int lo = max(row_begin, p.row_lo), hi = min(row_end, p.row_hi);
+  if (lo >= hi) return;
+  const int ta0 = lo >> 6, ta1 = (hi + 63) >> 6;
+  const int t0 = ta0 + blockIdx.x * p.rows_per_cta;      // rows_per_cta: here tiles per CTA
+  const int ntiles = max(0, min(ta1, t0 + p.rows_per_cta) - t0);
+  if (ntiles == 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    for (int i = 0; i < kFtStages; ++i) { mbar_init(&full[i], 1); mbar_init(&afull[i], 4); mbar_init(&empty[i], 1); }
+    mbar_init(tfull, 1);
+    mbar_fence_init();
   }
-  const int r0 = max(row_begin, p.row_lo) + blockIdx.x * p.rows_per_cta;
-  const int r1 = min(min(row_end, p.row_hi), r0 + p.rows_per_cta);
-  if (r0 >= r1) return;
-  float acc[PTPAD];
+  if (warp == 5) tmem_alloc(tmem_slot, 256);
+  // A boxes and the zero box start as zeros: builders only ever write the PTPAD/8 real 16-byte chunks of a row
+  for (int i = threadIdx.x; i < (kFtStages * 16384 + 8192) / 16; i += kFtThreads) {
+    const int st = i / 1024, o = i % 1024;
+    uint8_t* dst = st < kFtStages ? smem + (size_t)st * kStage + kBBytes + 2 * kTL : s_zero;
+    reinterpret_cast<uint4*>(dst)[o] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int it = 0; it < ntiles; ++it) {
+        const int st = it % kFtStages;
+        mbar_wait_idle(&empty[st], ((it / kFtStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[st], kBBytes + 2 * kTL);
+        uint8_t* dst = smem + (size_t)st * kStage;
+        const int ta = t0 + it;
 #pragma unroll
-  for (int k = 0; k < PTPAD; ++k) acc[k] = 0.f;
-  for (int rb = r0; rb < r1; rb += 32) {
-    const int nr = min(32, r1 - rb);
-    __syncthreads();
-    for (int idx = f; idx < 32 * PTPAD; idx += 256) {
-      const int r = idx & 31, k = idx >> 5;          // rows fastest: T and L are tiled [tile][slot][64 rows]
-      float v = 0.f;
-      if (r < nr) {
-        const float t = p.T[lfix_index(rb + r, k, PTPAD)];
-        if (t != 0.f) {
-          const int nfix = (int)p.lfix[lfix_index(rb + r, k, PTPAD)] >> 5;
-          const float c = ex2_approx((float)kCOff - (float)nfix * (1.f / (float)(1 << kLogShift)));
-          v = nfix < kNMax ? t / c : 0.f;              // relu gate: C == 0 never wins the max with u > 0
-        }
-      }
-      s_dc[r][k] = v;
-    }
-    __syncthreads();
-    for (int r8 = 0; r8 < nr; r8 += 8) {            // 8 independent global loads in flight per thread
-      float xv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = r8 + j;
-        xv[j] = r < nr ? __bfloat162float(p.h[(size_t)(rb + r - p.h_row0) * kD + f]) * __ldg(p.invn + rb + r) : 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4* dc4 = reinterpret_cast<const float4*>(&s_dc[r8 + j][0]);     // rows >= nr hold zeros
-#pragma unroll
-        for (int k4 = 0; k4 < PTPAD / 4; ++k4) {
-          const float4 dcv = dc4[k4];
-          acc[4 * k4 + 0] = fmaf(dcv.x, xv[j], acc[4 * k4 + 0]);
-          acc[4 * k4 + 1] = fmaf(dcv.y, xv[j], acc[4 * k4 + 1]);
-          acc[4 * k4 + 2] = fmaf(dcv.z, xv[j], acc[4 * k4 + 2]);
-          acc[4 * k4 + 3] = fmaf(dcv.w, xv[j], acc[4 * k4 + 3]);
-        }
+        for (int bx = 0; bx < 4; ++bx) tma_load_2d(dst + bx * (kBN * 128), &tm_x, &full[st], bx * 64, ta * 64 - p.h_row0);
+        bulk_load(dst + kBBytes, p.T + (size_t)ta * PTPAD * 64, kTL, &full[st]);
+        bulk_load(dst + kBBytes + kTL, p.lfix + (size_t)ta * PTPAD * 64, kTL, &full[st]);
       }
     }
-  }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 1, 1);
+      for (int it = 0; it < ntiles; ++it) {
+        const int st = it % kFtStages;
+        mbar_wait_idle(&afull[st], (it / kFtStages) & 1);      // implies full[st]: the builders waited for it
+        tc_fence_after();
+        const uint32_t sb = smem_u32(smem + (size_t)st * kStage);
+        const uint32_t sa = sb + kBBytes + 2 * kTL;
 #pragma unroll
-  for (int k = 0; k < PTPAD; ++k) {
+        for (int half = 0; half < 2; ++half) {                 // hi and lo parts of the A operand
+          const uint32_t sah = sa + half * 8192;
+          const uint32_t lbo_a = smem_u32(s_zero) - sah;       // second M box = the shared zero box
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                        // 16 rows per MMA; MN-major: +2048 B per 16 k-rows
+            const uint64_t ad = umma_desc_sw128(sah + k * 2048, lbo_a, 1024);
+            const uint64_t bd = umma_desc_sw128(sb + k * 2048, kBN * 128, 1024);
+            umma_f16(tmem_base, ad, bd, idesc, (it | half | k) != 0);
+          }
+        }
+        umma_commit(&empty[st]);
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    // ---------------- builders: dC tile as a bf16 MN-major A operand ----------------
+    const int tid = threadIdx.x;                               // 0..127
+    for (int it = 0; it < ntiles; ++it) {
+      const int st = it % kFtStages;
+      mbar_wait(&full[st], (it / kFtStages) & 1);
+      const uint8_t* base = smem + (size_t)st * kStage + kBBytes;
+      const float* sT = reinterpret_cast<const float*>(base);
+      const float* sL = reinterpret_cast<const float*>(base + kTL);
+      uint8_t* sA = const_cast<uint8_t*>(base) + 2 * kTL;
+      const int row0 = (t0 + it) * 64;
+      for (int item = tid; item < 64 * (PTPAD / 8); item += 128) {
+        const int r = item & 63, ch = item >> 6;
+        const bool ok = row0 + r >= lo && row0 + r < hi;
+        const float inv = ok ? __ldg(p.invn + row0 + r) : 0.f;
+        uint32_t w[4], wl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float v[2], vl[2];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int slot = ch * 8 + 2 * e + h2;
+            const float t = sT[slot * 64 + r];
+            const int nfix = (int)sL[slot * 64 + r] >> 5;
+            const float c = ex2_approx((float)kCOff - (float)nfix * (1.f / (float)(1 << kLogShift)));
+            v[h2] = (ok && t != 0.f && nfix < kNMax) ? t / c * inv : 0.f;   // relu gate: C == 0 never wins the max with u > 0
+            vl[h2] = v[h2] - __bfloat162float(__float2bfloat16_rn(v[h2]));
+          }
+          w[e] = pack_bf16x2(v[0], v[1]);
+          wl[e] = pack_bf16x2(vl[0], vl[1]);
+        }
+        const uint32_t off = r * 128 + ((ch ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(sA + off) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(sA + 8192 + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&afull[st]);
+    }
+    // ---------------- epilogue: lanes = token slots ----------------
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int slot = warp * 32 + lane;
     int tok = -1;
-    if (k < p.P1) tok = k;
-    else if (k >= p.P1pad && k - p.P1pad < p.P2) tok = p.P1 + k - p.P1pad;
-    if (tok >= 0 && acc[k] != 0.f) atomicAdd(p.dchat + ((size_t)b * Pt + tok) * kD + f, acc[k]);
+    if (slot < p.P1) tok = slot;
+    else if (slot >= p.P1pad && slot - p.P1pad < p.P2) tok = p.P1 + slot - p.P1pad;
+    if (warp * 32 < PTPAD) {                                   // warps whose lanes hold real slots
+#pragma unroll 1
+      for (int cc = 0; cc < 8; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cc * 32, v);
+        tmem_ld_wait();
+        if (tok >= 0) {
+          float* dst = p.dchat + ((size_t)b * Pt + tok) * kD + cc * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float a = __uint_as_float(v[j]);
+            if (a != 0.f) atomicAdd(dst + j, a);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -1000,18 +1106,37 @@ int launch_modularity_execute(const bf16* h_local, int local_rows, int row_lo, i
   fp.h = h_local; fp.invn = c.invn; fp.lfix = c.lfix; fp.T = c.T; fp.cu = cu; fp.s = c.s;
   fp.dchat = dchat; fp.loss = loss; fp.P1 = P1; fp.P2 = P2; fp.P1pad = P1pad;
   fp.row_lo = whole ? 0 : row_lo; fp.row_hi = whole ? INT_MAX : row_lo + local_rows; fp.h_row0 = row_lo;
-  const int fin_len = std::max(own_len, 1);
-  const int fin_chunks = std::max(1, std::min((fin_len + 255) / 256, (4 * imp_num_sms() + B - 1) / B));
-  fp.rows_per_cta = ((fin_len + fin_chunks - 1) / fin_chunks + 31) & ~31;
-  const dim3 fgrid((fin_len + fp.rows_per_cta - 1) / fp.rows_per_cta, B);
+  if (local_rows == 0) {        // a rank without rows of the bag: its partial sums are zero
+    IMP_CUDA(cudaMemsetAsync(loss, 0, (size_t)B * 2 * 4, st));
+    return IMP_OK;
+  }
+  // tcgen05 finish: about one CTA per SM, each over a contiguous run of absolute 64-row tiles of one bag
+  CUtensorMap th;          // the rows of h this call owns (out-of-range rows of a tile are zero-filled by TMA)
+  if ((rc = imp_make_tmap_2d(&th, h_local, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, (uint64_t)std::max(local_rows, 1), kD * 2, 64, kBN,
+                             CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  const int fin_tiles = (std::max(own_len, 1) + 63) / 64 + 1;
+  const int fin_chunks = std::max(1, std::min(fin_tiles, (imp_num_sms() + B - 1) / B));
+  fp.rows_per_cta = (fin_tiles + fin_chunks - 1) / fin_chunks;           // tiles per CTA
+  const dim3 fgrid((fin_tiles + fp.rows_per_cta - 1) / fp.rows_per_cta, B);
+#define IMP_FIN(PT)                                                                                                    \
+  do {                                                                                                                  \
+    constexpr size_t smem = finish_tc_smem<PT>();                                                                       \
+    static bool done = false;                                                                                           \
+    if (!done) {                                                                                                        \
+      IMP_CUDA(cudaFuncSetAttribute(modularity_finish_tc_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      done = true;                                                                                                      \
+    }                                                                                                                   \
+    IMP_LAUNCH("modularity_finish", st, modularity_finish_tc_kernel<PT><<<fgrid, kFtThreads, smem, st>>>(th, fp));     \
+  } while (0)
   switch (PtPad) {
-    case 8: IMP_LAUNCH("modularity_finish", st, modularity_finish_kernel<8><<<fgrid, 256, 0, st>>>(fp)); break;
-    case 16: IMP_LAUNCH("modularity_finish", st, modularity_finish_kernel<16><<<fgrid, 256, 0, st>>>(fp)); break;
-    case 24: IMP_LAUNCH("modularity_finish", st, modularity_finish_kernel<24><<<fgrid, 256, 0, st>>>(fp)); break;
-    case 32: IMP_LAUNCH("modularity_finish", st, modularity_finish_kernel<32><<<fgrid, 256, 0, st>>>(fp)); break;
-    case 40: IMP_LAUNCH("modularity_finish", st, modularity_finish_kernel<40><<<fgrid, 256, 0, st>>>(fp)); break;
+    case 8: IMP_FIN(8); break;
+    case 16: IMP_FIN(16); break;
+    case 24: IMP_FIN(24); break;
+    case 32: IMP_FIN(32); break;
+    case 40: IMP_FIN(40); break;
     default: IMP_FAIL(IMP_ERR_ARG, "modularity: unsupported padded token count %d", PtPad);
   }
+#undef IMP_FIN
   IMP_LAUNCH_CHECK();
   return IMP_OK;
 }
