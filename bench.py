@@ -31,7 +31,9 @@ GROUP_SIZES = [82, 330, 513, 440, 1538, 451]
 WORKLOAD = "configs[1]: survival training, synthetic TCGA-shaped bags 16384x512, 32 prototypes, 6 pathways, bf16"
 # dram__bytes_read.sum + dram__bytes_write.sum of one modularity_sweep launch from `ncu --set full`
 # (profiles/r01_ncu_full_final.md), keyed by bags per launch; None when not captured for that size
-SWEEP_TRAFFIC_PER_LAUNCH = {32: 424.2e6 + 61.9e6}
+SWEEP_TRAFFIC_PER_LAUNCH = {32: 425.6e6 + 61.5e6}
+# the same sum over one step's launches of the streaming kernels (path_net fwd, 2x pool fwd + merge, 2x dq, dz, dW1)
+STREAM_TRAFFIC_PER_STEP = {32: 3.26e9}
 
 
 def parse():
@@ -334,7 +336,7 @@ def run_ours(args):
     stream_ms = sum(pk_s[k]["ms_per_step"] for k in stream_names if k in pk_s)
     alg_stream = 2.0 * rows * D_IN * 2.0
     roofline_stream = {"bound": "hbm", "achieved": round(alg_stream / (stream_ms * 1e-3) / 1e9, 2) if stream_ms else None,
-                       "peak": hbm_peak, "unit": "GB/s", "traffic": None,
+                       "peak": hbm_peak, "unit": "GB/s", "traffic": STREAM_TRAFFIC_PER_STEP.get(B),
                        "kernels": [k for k in stream_names if k in pk_s], "kernel_ms_per_step": round(stream_ms, 4),
                        "algorithmic_bytes_per_step": alg_stream}
     if roofline_stream["achieved"]:
