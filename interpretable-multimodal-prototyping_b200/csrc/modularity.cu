@@ -581,9 +581,9 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   // blocking: the item tile `it` needs has been issued (its gates only depend on strictly older tiles)
   auto ensure = [&](int it) {
     while (nis <= it) {
-      if (role_l) { mbar_wait(&lempty[nis % kLStages], ((nis / kLStages) & 1) ^ 1); issue_l(); }
-      else if (role_b) { mbar_wait(bempty, (nis & 1) ^ 1); issue_b(); }
-      else { mbar_wait(bfull, nis & 1); mbar_wait(&tempty[nis % kTBufs], ((nis / kTBufs) & 1) ^ 1); issue_mma(); }
+      if (role_l) { mbar_wait_idle(&lempty[nis % kLStages], ((nis / kLStages) & 1) ^ 1, 2000u); issue_l(); }
+      else if (role_b) { mbar_wait_idle(bempty, (nis & 1) ^ 1, 2000u); issue_b(); }
+      else { mbar_wait_idle(bfull, nis & 1, 2000u); mbar_wait_idle(&tempty[nis % kTBufs], ((nis / kTBufs) & 1) ^ 1, 2000u); issue_mma(); }
     }
   };
   const bool driver = role_l || role_b || role_m;
