@@ -52,8 +52,10 @@ def parse():
     ap.add_argument("--missing-omics", type=float, default=0.0,
                     help="configs[2]: fraction of slides whose genomics are missing (gene values imputed by the cohort means "
                          "in the encoder gather, umeml_gan.py:391-392); 0 = fully paired batches (configs[1])")
-    ap.add_argument("--workload", default="fusion", choices=["fusion", "kmeans"],
-                    help="fusion: the headline (configs[1]); kmeans: configs[4], 2^20 x 512 fp32 -> 32 centroids, one assignment pass per step")
+    ap.add_argument("--workload", default="fusion", choices=["fusion", "kmeans", "giant"],
+                    help="fusion: the headline (configs[1]); kmeans: configs[4], 2^20 x 512 fp32 -> 32 centroids, one assignment pass "
+                         "per step; giant: configs[3], ONE 120k-patch bag sharded by rows over the ranks (LSE-merged pooling, "
+                         "two-phase modularity), fwd+bwd per step")
     return ap.parse_args()
 
 
@@ -467,6 +469,82 @@ def run_kmeans(args):
     }))
 
 
+def run_giant(args):
+    """BASELINE.json configs[3]: giant-bag stress, 120 000 patches x 512 in ONE slide, 32 prototypes, sharded by
+    rows over the ranks of the box: every pooling block exchanges its (pooled, lse) state once and merges it with
+    the log-sum-exp kernel; the modularity term runs as prepare -> exchange -> sweep of the local row blocks.
+    A step = forward + backward of that one bag (strong scaling: the bag is fixed, the ranks split it)."""
+    import torch
+    import torch.distributed as dist
+    from imp_b200 import _lib, model as M, modularity as MOD, ops, parallel as PAR
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, P = 120000, args.protos
+    torch.manual_seed(1234)                                   # identical parameters on every rank
+    net = M.IMPHotPath(n_proto=P, dropout=0.25, seed=0).to(dev).train()
+    a, b = PAR.shard_bounds(n, world)[rank]
+    gen = torch.Generator(device=dev).manual_seed(100)
+    x = torch.randn(b - a, D_IN, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + rank)).bfloat16()
+    cot = torch.randn(1, P, 256, device=dev, generator=gen) * 1e-2
+    cu = torch.tensor([0, b - a], dtype=torch.int32, device=dev)
+    group = dist.group.WORLD if world > 1 else None
+    params = [p for p in net.parameters()]
+    blocks = [ops.block_params(blk) for blk in net.proto_g_blocks]
+
+    def step():
+        for p in params:
+            p.grad = None
+        c, h = ops.proto_fusion(x, cu, max(1, b - a), net.p_proto, net.path_net[0].weight, net.path_net[0].bias, blocks,
+                                p_drop=0.25, seed=net._seed(), shard_group=group)
+        loss = (c * cot).sum()
+        if world > 1:
+            loss = loss + MOD.modularity_terms_sharded(h, a, n, c, group=group)[0, 0]
+        else:
+            loss = loss + MOD.modularity_terms(h, cu, n, c)[0, 0]
+        loss.backward()
+        return c
+
+    for _ in range(max(1, args.warmup)):
+        c = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _lib.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        c = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - l0
+    agree = 0.0
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+        cs = [torch.empty_like(c) for _ in range(world)]
+        dist.all_gather(cs, c.contiguous())
+        agree = max(float((ci - cs[0]).abs().max().item()) for ci in cs)    # merged tokens are identical on every rank
+    if rank == 0:
+        print(json.dumps({
+            "metric": "giant_bags_per_s_fwd_bwd", "value": args.steps / (ms * 1e-3), "unit": "bags/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[3]: giant-bag stress, 1 slide of 120000x512 patches, %d prototypes, rows sharded over %d GPU(s)" % (P, world),
+                       "modularity": True, "dropout": 0.25, "l2": "inputs larger than L2: %.0f MiB of bf16 features per rank" % ((b - a) * D_IN * 2 / 2 ** 20),
+                       "parallelism": "rows%d" % world},
+            "max_abs_token_difference_between_ranks": agree, "gpu_launches": int(launches),
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     # Exactly one line on stdout: libraries (NCCL prints its version banner there) write to fd 1 behind Python's
@@ -477,6 +555,8 @@ def main():
     sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.workload == "kmeans":
         run_kmeans(args)
+    elif args.workload == "giant":
+        run_giant(args)
     elif args.impl == "reference":
         run_reference(args)
     else:
