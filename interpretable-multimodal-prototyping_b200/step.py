@@ -73,6 +73,11 @@ class GraphedStep:
             loss.backward()
             return loss
 
+        # the warm-up below runs on a side stream on purpose; AccumulateGrad nodes of earlier eager steps may still
+        # be bound to the default stream, which is harmless here
+        setw = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if setw is not None:
+            setw(False)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                              # warm-up off the capture stream (allocator, attributes)
