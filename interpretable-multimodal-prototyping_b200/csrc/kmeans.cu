@@ -163,9 +163,10 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap tm_x, const KmParams p)
 // epilogue adds the three groups, small ones first.  The CUDA cores only split the stream
 // (4.5 instructions per element: two masks, two packed subtractions, three byte permutes per pair), so the kernel
 // is bound by HBM instead of by the fp32 pipe.
-//   warps 0-7  : split the fp32 TMA tile [128 rows][64 features] into three bf16 K-major operand tiles, |x|^2,
+//   warps 0-7  : split the fp32 TMA boxes [128 rows][32 features] into three bf16 K-major operand tiles (the two
+//                feature halves of a 64-wide chunk are pipelined against the MMAs of the other half), |x|^2,
 //                and (warps 0-3, thread = row) the arg-min epilogue from TMEM
-//   warp 8     : TMA producer (2 stages);   warp 9 : MMA issuer (3 x parts x 4 k-steps per 64-feature chunk, N = 3 KP)
+//   warp 8     : TMA producer (4 box slots);   warp 9 : MMA issuer (3 x parts x 2 k-steps per half chunk, N = 3 KP)
 // ------------------------------------------------------------------------------------------
 constexpr int kTcRows = 128;
 constexpr int kTcKC = 64;                                  // features per chunk
@@ -223,19 +224,19 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const KmTcPara
   float* s_m2 = reinterpret_cast<float*>(s_mu + (size_t)nchunks * kMuBox);
   float* s_xx = s_m2 + KP;                                 // [128] upper-half partial of |x|^2
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_xx + kTcRows);
-  uint64_t* xfull = bars;          // [2] TMA -> splitters
-  uint64_t* xempty = bars + 2;     // [2] 8 warps -> TMA
-  uint64_t* pfull = bars + 4;      // 8 warps -> MMA (operand tiles written)
-  uint64_t* pempty = bars + 5;     // MMA commit -> splitters
-  uint64_t* tfull = bars + 6;      // [2] MMA -> epilogue
-  uint64_t* tempty = bars + 8;     // [2] 4 warps -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* xfull = bars;          // [4] TMA -> splitters, one slot = one [128][32 floats] box = half a chunk
+  uint64_t* xempty = bars + 4;     // [4] 8 warps -> TMA
+  uint64_t* pfull = bars + 8;      // [2] 8 warps -> MMA: operand tiles of feature half 0 / 1 written
+  uint64_t* pempty = bars + 10;    // [2] MMA commit -> splitters
+  uint64_t* tfull = bars + 12;     // [2] MMA -> epilogue
+  uint64_t* tempty = bars + 14;    // [2] 4 warps -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_x);
-    for (int i = 0; i < 2; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 8); mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
-    mbar_init(pfull, 8); mbar_init(pempty, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&pfull[i], 8); mbar_init(&pempty[i], 1); mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     mbar_fence_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, 256);
@@ -273,15 +274,13 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const KmTcPara
 
   if (warp == 8) {
     if (lane == 0) {
-      int g = 0;
+      int hh = 0;                                          // half-chunk counter: ring slot = hh & 3
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
-        for (int c = 0; c < nchunks; ++c, ++g) {
-          const int s = g & 1;
-          mbar_wait_idle(&xempty[s], ((g >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&xfull[s], kTcXStage);
-          uint8_t* dst = s_x + (size_t)s * kTcXStage;
-          tma_load_2d(dst, &tm_x, &xfull[s], c * kTcKC, tile * kTcRows);
-          tma_load_2d(dst + kTcRows * 128, &tm_x, &xfull[s], c * kTcKC + 32, tile * kTcRows);
+        for (int c2 = 0; c2 < 2 * nchunks; ++c2, ++hh) {
+          const int s = hh & 3;
+          mbar_wait_idle(&xempty[s], ((hh >> 2) & 1) ^ 1);
+          mbar_arrive_expect_tx(&xfull[s], kTcRows * 128);
+          tma_load_2d(s_x + (size_t)s * (kTcRows * 128), &tm_x, &xfull[s], c2 * 32, tile * kTcRows);
         }
     }
   } else if (warp == 9) {
@@ -293,61 +292,68 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const KmTcPara
         const int acc = ti & 1;
         mbar_wait_idle(&tempty[acc], ((ti >> 1) & 1) ^ 1);
         for (int c = 0; c < nchunks; ++c, ++g) {
-          mbar_wait_idle(pfull, g & 1);
-          tc_fence_after();
           const uint32_t sb = sm + c * kMuBox;
 #pragma unroll
-          for (int t = 2; t >= 0; --t) {                   // x parts, smallest first: xl, xm, xh
-            const uint32_t sa = sp + t * kTcPart;
+          for (int half = 0; half < 2; ++half) {           // the two 32-feature halves of the chunk are pipelined
+            mbar_wait_idle(&pfull[half], g & 1);
+            tc_fence_after();
 #pragma unroll
-            for (int ks = 0; ks < kTcKC / 16; ++ks)
-              umma_f16(tmem_base + acc * 128, umma_desc_sw128(sa + ks * 32, 0, 1024), umma_desc_sw128(sb + ks * 32, 0, 1024),
-                       idesc, (c != 0) || (t != 2) || (ks != 0));
+            for (int t = 2; t >= 0; --t) {                 // x parts, smallest first: xl, xm, xh
+              const uint32_t sa = sp + t * kTcPart;
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2) {
+                const int ks = half * 2 + k2;
+                umma_f16(tmem_base + acc * 128, umma_desc_sw128(sa + ks * 32, 0, 1024), umma_desc_sw128(sb + ks * 32, 0, 1024),
+                         idesc, (c != 0) || (half != 0) || (t != 2) || (k2 != 0));
+              }
+            }
+            umma_commit(&pempty[half]);
           }
-          umma_commit(pempty);
         }
         umma_commit(&tfull[acc]);
       }
     }
   } else {
     // ---------------- splitters: thread = (row, 32-feature half of the chunk) ----------------
-    const int r = threadIdx.x & 127, hf = threadIdx.x >> 7;
+    const int r = threadIdx.x & 127, hf = threadIdx.x >> 7;   // hf: which 16 of the 32 features of a half-chunk
     const bool want_dist = p.best_dist != nullptr;         // |x|^2 is the same for every centroid: only the distance output needs it
-    int g = 0, ti = 0;
+    int g = 0, ti = 0, hh = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
       float xx = 0.f;
       for (int c = 0; c < nchunks; ++c, ++g) {
-        const int s = g & 1;
-        mbar_wait(&xfull[s], (g >> 1) & 1);
-        const uint8_t* xrow = s_x + (size_t)s * kTcXStage + hf * (kTcRows * 128) + r * 128;
-        float v[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 q4 = *reinterpret_cast<const float4*>(xrow + ((j ^ (r & 7)) << 4));
-          v[4 * j] = q4.x; v[4 * j + 1] = q4.y; v[4 * j + 2] = q4.z; v[4 * j + 3] = q4.w;
-        }
-        // (the fp32 stage is released at the END of the chunk: releasing it right after these loads let the next TMA
-        //  write race with them -- a few rows per tile came out wrong once a stage was reused)
-        mbar_wait(pempty, (g & 1) ^ 1);                    // MMAs of the previous chunk have read the operand tiles
+        for (int half = 0; half < 2; ++half, ++hh) {
+          const int s = hh & 3;
+          mbar_wait(&xfull[s], (hh >> 2) & 1);
+          const uint8_t* xrow = s_x + (size_t)s * (kTcRows * 128) + r * 128;
+          float v[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                      // 8 features -> one 16-byte chunk per part
-          uint32_t w[3][4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            split3x2(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], w[0][e], w[1][e], w[2][e]);
-            if (want_dist) {
-              xx = fmaf(v[8 * j + 2 * e], v[8 * j + 2 * e], xx);
-              xx = fmaf(v[8 * j + 2 * e + 1], v[8 * j + 2 * e + 1], xx);
-            }
+          for (int j = 0; j < 4; ++j) {
+            const float4 q4 = *reinterpret_cast<const float4*>(xrow + (((hf * 4 + j) ^ (r & 7)) << 4));
+            v[4 * j] = q4.x; v[4 * j + 1] = q4.y; v[4 * j + 2] = q4.z; v[4 * j + 3] = q4.w;
           }
-          const uint32_t off = (uint32_t)(r * 128 + (((hf * 4 + j) ^ (r & 7)) << 4));
+          mbar_wait(&pempty[half], (g & 1) ^ 1);           // the MMAs of the previous chunk have read this half of the tiles
 #pragma unroll
-          for (int part = 0; part < 3; ++part)
-            *reinterpret_cast<uint4*>(s_parts + part * kTcPart + off) = make_uint4(w[part][0], w[part][1], w[part][2], w[part][3]);
+          for (int j = 0; j < 2; ++j) {                    // 8 features -> one 16-byte chunk per part
+            uint32_t w[3][4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              split3x2(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], w[0][e], w[1][e], w[2][e]);
+              if (want_dist) {
+                xx = fmaf(v[8 * j + 2 * e], v[8 * j + 2 * e], xx);
+                xx = fmaf(v[8 * j + 2 * e + 1], v[8 * j + 2 * e + 1], xx);
+              }
+            }
+            const uint32_t off = (uint32_t)(r * 128 + (((half * 4 + hf * 2 + j) ^ (r & 7)) << 4));
+#pragma unroll
+            for (int part = 0; part < 3; ++part)
+              *reinterpret_cast<uint4*>(s_parts + part * kTcPart + off) = make_uint4(w[part][0], w[part][1], w[part][2], w[part][3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          // the fp32 slot is released only now: releasing it right after the loads let the next TMA write race with them
+          if (lane == 0) { mbar_arrive(&pfull[half]); mbar_arrive(&xempty[s]); }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(pfull); mbar_arrive(&xempty[s]); }
       }
       // ---------------- epilogue: thread = row (warps 0-3) ----------------
       if (p.best_dist) {
