@@ -301,6 +301,9 @@ def run_ours(args):
         "pool_fwd": ("hbm", rows * 256 * 2.0), "pool_bwd_dq": ("hbm", rows * 256 * 2.0),
         "pool_bwd_dz": ("hbm", rows * 256 * 2.0 * 2),
         "modularity_degrees_gram": ("tensor", 2.0 * B * N * N * 256), "modularity_sweep": ("tensor", 2.0 * B * N * N * 256),
+        # O(N) kernels of the modularity term: bytes they have to move (h read, xh + assignments written / read back)
+        "modularity_prep": ("hbm", rows * (256 * 2.0 * 2 + 40 * 4.0)), "modularity_degrees_closed": ("hbm", rows * 256 * 2.0),
+        "modularity_finish": ("hbm", rows * (256 * 2.0 + 2 * 40 * 4.0)),
     }
     kernels_out = []
     tot_kernel_ms = sum(v["ms_per_step"] for v in pk.values()) or 1.0
