@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
     "-DIMP_BUILD", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("IMP_NVCC_EXTRA", "").split()      # e.g. IMP_NVCC_EXTRA=-DIMP_SWEEP_TRACE for the debug counters
 
 
 def _nvcc() -> str:

@@ -115,6 +115,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Wait used by the single-thread producer / MMA-issuer roles: the hardware suspends the thread for up
 // to `hint_ns` per probe instead of spinning, so the idle role does not steal issue slots from the
 // epilogue warps that share its scheduler.
+// one lane of a CONVERGED warp.  Asynchronous-proxy instructions (UTCHMMA, UTMALDG, UBLKCP, UTCBAR) take their
+// operands from uniform registers: inside an elect.sync-guarded block ptxas knows a single lane is active and
+// uses them directly; behind `lane == 0` it emits a per-lane waterfall loop around every such instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 20000u) {
   uint32_t addr = smem_u32(bar);
   asm volatile(

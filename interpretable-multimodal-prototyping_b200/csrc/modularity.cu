@@ -474,6 +474,9 @@ modularity_degrees_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
 // ------------------------------------------------------------------------------------------
 constexpr int kSwWarps = 16;
 constexpr int kSwThreads = kSwWarps * 32;           // 512
+#ifdef IMP_SWEEP_TRACE
+__device__ unsigned long long g_sweep_trace[16 * 8];   // debug counters (profiles/r01_sweep_iterations.md)
+#endif
 constexpr int kLStages = 4;
 constexpr int kTBufs = 4;                           // TMEM accumulator buffers of 64 columns
 
@@ -533,64 +536,89 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // Three single-thread roles, spread over three warps that sit on different scheduler sub-partitions so that
-  // no warp carries all of the issue overhead (one driver warp for everything ran ~35% behind the other 15 and
-  // paced the whole CTA).  The roles only talk through mbarriers:
+  // Three roles, spread over three warps that sit on different scheduler sub-partitions so that no warp carries
+  // all of the issue overhead (one driver warp for everything ran ~35% behind the other 15 and paced the whole
+  // CTA).  A role is executed by its whole warp, converged, and the asynchronous instruction itself by the lane
+  // elect.sync picks: inside an elect-guarded block ptxas keeps descriptors and barrier addresses in uniform
+  // registers (~45 instructions for the 16 MMAs of a tile); behind a `lane == 0` test it wraps every UTCHMMA /
+  // UTMALDG in a per-lane waterfall loop (~220 instructions), which made the MMA warp the slowest of the CTA by 16%.
+  // The roles only talk through mbarriers:
   //   role L  (warp 15): bulk copies of the L/degree tiles, gated by lempty
   //   role B  (warp 14): TMA load of the B box, gated by bempty (= the MMA of the previous tile has retired)
   //   role M  (warp 13): tcgen05 MMA, gated by bfull and tempty; commits to bempty and tfull
-  const bool role_l = (warp == kSwWarps - 1 && lane == 0);
-  const bool role_b = (warp == kSwWarps - 2 && lane == 0);
-  const bool role_m = (warp == kSwWarps - 3 && lane == 0);
-  int nis = 0;                                         // tiles issued by this thread's role
+  const bool role_l = (warp == kSwWarps - 1);
+  const bool role_b = (warp == kSwWarps - 2);
+  const bool role_m = (warp == kSwWarps - 3);
+  int nis = 0;                                         // tiles issued by this warp's role (warp-uniform)
   auto issue_l = [&]() {
-    const int ls = nis % kLStages;
-    mbar_arrive_expect_tx(&lfull[ls], kLStage);
-    uint8_t* dst = s_l + (size_t)ls * kLStage;
-    const int ta = t0 + nis;
-    bulk_load(dst, p.lfix + (size_t)ta * PtPad * 64, kLBytes, &lfull[ls]);
-    bulk_load(dst + kLBytes, p.d + (size_t)ta * 64, kBN * 4, &lfull[ls]);
+    if (elect_one()) {
+      const int ls = nis % kLStages;
+      mbar_arrive_expect_tx(&lfull[ls], kLStage);
+      uint8_t* dst = s_l + (size_t)ls * kLStage;
+      const int ta = t0 + nis;
+      bulk_load(dst, p.lfix + (size_t)ta * PtPad * 64, kLBytes, &lfull[ls]);
+      bulk_load(dst + kLBytes, p.d + (size_t)ta * 64, kBN * 4, &lfull[ls]);
+    }
     ++nis;
   };
   auto issue_b = [&]() {
-    mbar_arrive_expect_tx(bfull, kBBytes);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bfull, kBBytes);
 #pragma unroll
-    for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_b + bx * (kBN * 128), &tm_b, bfull, bx * 64, (t0 + nis) * kBN);
+      for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_b + bx * (kBN * 128), &tm_b, bfull, bx * 64, (t0 + nis) * kBN);
+    }
     ++nis;
   };
   auto issue_mma = [&]() {
-    constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
     tc_fence_after();
-    const uint64_t ad0 = umma_desc_sw128(smem_u32(s_a), 0, 1024), bd0 = umma_desc_sw128(smem_u32(s_b), 0, 1024);
-    const uint32_t tacc = tmem_base + (nis % kTBufs) * kBN;
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
+      const uint64_t ad0 = umma_desc_sw128(smem_u32(s_a), 0, 1024), bd0 = umma_desc_sw128(smem_u32(s_b), 0, 1024);
+      const uint32_t tacc = tmem_base + (nis % kTBufs) * kBN;
 #pragma unroll
-    for (int k = 0; k < kD / 16; ++k)      // descriptor start addresses advance in 16-byte units
-      umma_f16(tacc, ad0 + (uint64_t)(((k >> 2) * (kBM * 128) + (k & 3) * 32) >> 4),
-               bd0 + (uint64_t)(((k >> 2) * (kBN * 128) + (k & 3) * 32) >> 4), idesc, k != 0);
-    umma_commit(bempty);
-    umma_commit(&tfull[nis % kTBufs]);
+      for (int k = 0; k < kD / 16; ++k)      // descriptor start addresses advance in 16-byte units
+        umma_f16(tacc, ad0 + (uint64_t)(((k >> 2) * (kBM * 128) + (k & 3) * 32) >> 4),
+                 bd0 + (uint64_t)(((k >> 2) * (kBN * 128) + (k & 3) * 32) >> 4), idesc, k != 0);
+      umma_commit(bempty);
+      umma_commit(&tfull[nis % kTBufs]);
+    }
     ++nis;
   };
-  // non-blocking: issue the next item of this thread's role if its gate is open
+  // non-blocking: issue the next item of this warp's role if its gate is open (every lane probes, so the answer
+  // and with it nis stay warp-uniform)
   auto poll = [&]() {
     if (nis >= ntiles) return;
-    if (role_l) { if (mbar_test(&lempty[nis % kLStages], ((nis / kLStages) & 1) ^ 1)) issue_l(); }
-    else if (role_b) { if (mbar_test(bempty, (nis & 1) ^ 1)) issue_b(); }
-    else if (mbar_test(bfull, nis & 1) && mbar_test(&tempty[nis % kTBufs], ((nis / kTBufs) & 1) ^ 1)) issue_mma();
+    bool open;
+    if (role_l) open = mbar_test(&lempty[nis % kLStages], ((nis / kLStages) & 1) ^ 1);
+    else if (role_b) open = mbar_test(bempty, (nis & 1) ^ 1);
+    else open = mbar_test(bfull, nis & 1) && mbar_test(&tempty[nis % kTBufs], ((nis / kTBufs) & 1) ^ 1);
+    if (__all_sync(0xffffffffu, open)) {
+      if (role_l) issue_l(); else if (role_b) issue_b(); else issue_mma();
+    }
+    __syncwarp();
   };
   // blocking: the item tile `it` needs has been issued (its gates only depend on strictly older tiles)
   auto ensure = [&](int it) {
     while (nis <= it) {
-      if (role_l) { mbar_wait_idle(&lempty[nis % kLStages], ((nis / kLStages) & 1) ^ 1, 2000u); issue_l(); }
-      else if (role_b) { mbar_wait_idle(bempty, (nis & 1) ^ 1, 2000u); issue_b(); }
-      else { mbar_wait_idle(bfull, nis & 1, 2000u); mbar_wait_idle(&tempty[nis % kTBufs], ((nis / kTBufs) & 1) ^ 1, 2000u); issue_mma(); }
+      if (role_l) { mbar_wait_idle(&lempty[nis % kLStages], ((nis / kLStages) & 1) ^ 1, 2000u); __syncwarp(); issue_l(); }
+      else if (role_b) { mbar_wait_idle(bempty, (nis & 1) ^ 1, 2000u); __syncwarp(); issue_b(); }
+      else {
+        mbar_wait_idle(bfull, nis & 1, 2000u);
+        mbar_wait_idle(&tempty[nis % kTBufs], ((nis / kTBufs) & 1) ^ 1, 2000u);
+        __syncwarp();
+        issue_mma();
+      }
+      __syncwarp();
     }
   };
   const bool driver = role_l || role_b || role_m;
   if (role_m) {
-    mbar_arrive_expect_tx(afull, kABytes);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(afull, kABytes);
 #pragma unroll
-    for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_a + bx * (kBM * 128), &tm_a, afull, bx * 64, i0);
+      for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_a + bx * (kBM * 128), &tm_a, afull, bx * 64, i0);
+    }
+    __syncwarp();
     mbar_wait(afull, 0);
   }
 
@@ -619,14 +647,32 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   const float2 one2 = make_float2(1.f, 1.f), neg2 = make_float2(-1.f, -1.f);
   float2 sg[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 
+#ifdef IMP_SWEEP_TRACE
+  long long tr_t = 0, tr_l = 0, tr_e = 0, tr_look = 0;
+  const long long tr_start = clock64();
+#endif
   for (int it = 0; it < ntiles; ++it) {
     const int tb = it % kTBufs, ls = it % kLStages;
+#ifdef IMP_SWEEP_TRACE
+    const long long c0t = clock64();
+#endif
     if (driver) { ensure(it); poll(); }
     __syncwarp();
+#ifdef IMP_SWEEP_TRACE
+    const long long c1t = clock64();
+    tr_look += driver ? nis - it : 0;
+#endif
     // suspended waits: a warp that ran ahead must not spin away the issue slots of the warps it is waiting for
     mbar_wait_idle(&tfull[tb], (it / kTBufs) & 1, 4000u);
     tc_fence_after();
+#ifdef IMP_SWEEP_TRACE
+    const long long c2t = clock64();
+#endif
     mbar_wait_idle(&lfull[ls], (it / kLStages) & 1, 4000u);
+#ifdef IMP_SWEEP_TRACE
+    const long long c3t = clock64();
+    tr_e += c1t - c0t; tr_t += c2t - c1t; tr_l += c3t - c2t;
+#endif
     const uint8_t* st = s_l + (size_t)ls * kLStage;
     const float4* sL = reinterpret_cast<const float4*>(st) + hc * 4;               // [token][16 float4]: + token*16 + g
     const float4* sd = reinterpret_cast<const float4*>(st + kLBytes) + hc * 4;
@@ -710,6 +756,16 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     __syncwarp();
     if (lane == 0) mbar_arrive(&lempty[ls]);
   }
+#ifdef IMP_SWEEP_TRACE
+  if (lane == 0) {     // per warp: cycles waiting for the accumulator / the L tile / inside ensure(), loop cycles, tiles, look-ahead
+    atomicAdd(&g_sweep_trace[warp * 8 + 0], (unsigned long long)tr_t);
+    atomicAdd(&g_sweep_trace[warp * 8 + 1], (unsigned long long)tr_l);
+    atomicAdd(&g_sweep_trace[warp * 8 + 2], (unsigned long long)(clock64() - tr_start));
+    atomicAdd(&g_sweep_trace[warp * 8 + 3], (unsigned long long)ntiles);
+    atomicAdd(&g_sweep_trace[warp * 8 + 4], (unsigned long long)tr_look);
+    atomicAdd(&g_sweep_trace[warp * 8 + 5], (unsigned long long)tr_e);
+  }
+#endif
   // ---------------- flush ----------------
   {
     const float inv_gs4 = 1.f / gs4;
@@ -1149,3 +1205,11 @@ int launch_modularity(const bf16* h, int total_rows, const int* cu, int B, int m
   if ((rc = launch_modularity_prepare(h, total_rows, 0, total_rows, cu, B, chat, P1, P2, workspace, st))) return rc;
   return launch_modularity_execute(h, total_rows, 0, total_rows, cu, B, max_len, P1, P2, temp, workspace, loss, dchat, st);
 }
+
+#ifdef IMP_SWEEP_TRACE
+extern "C" int imp_debug_sweep_trace(unsigned long long* host_out, int reset) {
+  if (host_out) cudaMemcpyFromSymbol(host_out, g_sweep_trace, sizeof(unsigned long long) * 128);
+  if (reset) { static unsigned long long z[128] = {0}; cudaMemcpyToSymbol(g_sweep_trace, z, sizeof(z)); }
+  return 0;
+}
+#endif
