@@ -462,10 +462,11 @@ modularity_degrees_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
 // Pair sweep (the trace and T): the dominant kernel of the training step.
 //   CTA = 128 rows (bag-relative block) x a range of ABSOLUTE 64-column tiles; 16 warps, thread = (row i, 16 of
 //   the 64 columns, four at a time), 128 registers per thread (a 17th warp would cap every thread at 96).
-//   No dedicated producer / MMA warps: the pair work of a tile takes microseconds, so lane 0 of warp 0 drives the
-//   asynchronous machinery from inside the sweep with non-blocking mbarrier probes (four poll points per tile):
-//   bulk copies of the L/degree tiles (4 stages), the TMA load of the B box (1 stage: it is free again as soon
-//   as its MMA retires) and the tcgen05 MMA 128x64x256 into one of four TMEM buffers, up to three tiles ahead.
+//   No dedicated producer / MMA warps: the pair work of a tile takes microseconds, so the sweep warps drive the
+//   asynchronous machinery themselves, in rotation, with non-blocking mbarrier probes (five probe points per
+//   tile): bulk copies of the L/degree tiles and the tcgen05 MMA 128x64x256 into a ring of four slots (TMEM
+//   accumulator + L tile), up to three tiles ahead, and the TMA load of the B box (1 stage: it is free again as
+//   soon as its MMA retires).
 //   Per four columns a thread runs
 //     - the (min,+) contraction over tokens: per token pair 2 broadcast 128-bit loads of L (token-major tile),
 //       4 FADD2 (two columns each, row operand broadcast) and 4 FMNMX3 (one per column chain);
@@ -477,8 +478,8 @@ constexpr int kSwThreads = kSwWarps * 32;           // 512
 #ifdef IMP_SWEEP_TRACE
 __device__ unsigned long long g_sweep_trace[16 * 8];   // debug counters (profiles/r01_sweep_iterations.md)
 #endif
-constexpr int kLStages = 4;
-constexpr int kTBufs = 4;                           // TMEM accumulator buffers of 64 columns
+constexpr int kTBufs = 4;                           // ring slots: TMEM accumulator of 64 columns + L/degree tile
+constexpr int kLStages = kTBufs;
 
 template <int NQ1, int NQ2>
 constexpr size_t sweep_smem() {
@@ -510,6 +511,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   uint64_t* afull = lempty + kLStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
   float* s_red = reinterpret_cast<float*>(tmem_slot + 2);                 // [16][2]
+  volatile int* s_mcnt = reinterpret_cast<volatile int*>(s_red + 2 * kSwWarps);
 
   const int b = blockIdx.z;
   const int row_begin = __ldg(p.cu + b), row_end = __ldg(p.cu + b + 1);
@@ -529,6 +531,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     for (int i = 0; i < kTBufs; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kSwWarps); }
     for (int i = 0; i < kLStages; ++i) { mbar_init(&lfull[i], 1); mbar_init(&lempty[i], kSwWarps); }
     mbar_init(afull, 1);
+    *s_mcnt = 0;
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, kTBufs * kBN);
@@ -536,91 +539,93 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // Three roles, spread over three warps that sit on different scheduler sub-partitions so that no warp carries
-  // all of the issue overhead (one driver warp for everything ran ~35% behind the other 15 and paced the whole
-  // CTA).  A role is executed by its whole warp, converged, and the asynchronous instruction itself by the lane
-  // elect.sync picks: inside an elect-guarded block ptxas keeps descriptors and barrier addresses in uniform
-  // registers (~45 instructions for the 16 MMAs of a tile); behind a `lane == 0` test it wraps every UTCHMMA /
-  // UTMALDG in a per-lane waterfall loop (~220 instructions), which made the MMA warp the slowest of the CTA by 16%.
-  // The roles only talk through mbarriers:
-  //   role L  (warp 15): bulk copies of the L/degree tiles, gated by lempty
-  //   role B  (warp 14): TMA load of the B box, gated by bempty (= the MMA of the previous tile has retired)
-  //   role M  (warp 13): tcgen05 MMA, gated by bfull and tempty; commits to bempty and tfull
-  const bool role_l = (warp == kSwWarps - 1);
-  const bool role_b = (warp == kSwWarps - 2);
-  const bool role_m = (warp == kSwWarps - 3);
-  int nis = 0;                                         // tiles issued by this warp's role (warp-uniform)
-  auto issue_l = [&]() {
-    if (elect_one()) {
-      const int ls = nis % kLStages;
-      mbar_arrive_expect_tx(&lfull[ls], kLStage);
-      uint8_t* dst = s_l + (size_t)ls * kLStage;
-      const int ta = t0 + nis;
-      bulk_load(dst, p.lfix + (size_t)ta * PtPad * 64, kLBytes, &lfull[ls]);
-      bulk_load(dst + kLBytes, p.d + (size_t)ta * 64, kBN * 4, &lfull[ls]);
-    }
-    ++nis;
-  };
-  auto issue_b = [&]() {
+  // Producer work rotates over the 16 warps: warp n % 16 owns tile n and, from inside its own sweep, at non-blocking
+  // probe points (five per tile), performs
+  //   step 1 (gates: tiles < n issued, B box n landed, ring slot n % 4 released by all 16 warps):
+  //           bulk copies of the L / degree tile n, the 16 tcgen05 MMAs of tile n, commits to bempty and tfull;
+  //   step 2 (gate: the MMAs of tile n have retired = bempty): TMA load of B box n + 1 (single stage).
+  // Every step runs on a whole, converged warp and the asynchronous instructions on the lane elect.sync picks:
+  // inside an elect-guarded block ptxas keeps descriptors and barrier addresses in uniform registers (~45
+  // instructions for the 16 MMAs); behind a `lane == 0` test it wraps every UTCHMMA / UTMALDG in a per-lane
+  // waterfall loop (~220).  Pinned roles (MMA on warp 13, B on 14, L on 15) made those warps the slowest of the
+  // CTA - each mbarrier probe is a round trip through the busy shared-memory pipe, and the MMA issue stalls its
+  // warp - and the other warps then sat at the accumulator barrier for 15% of the kernel (IMP_SWEEP_TRACE).
+  // s_mcnt = number of tiles issued: bfull is one barrier whose phase flips every tile, so it may only be probed
+  // for tile n once tile n-1 has been issued (before that, parity n&1 still reads as phase n-2).
+  int m_next = warp;                                   // next tile this warp owns (step 1 pending)
+  int b_pend = -1;                                     // tile whose step 2 is pending, or -1
+  auto issue_b = [&](int n) {                          // B box of tile n
     if (elect_one()) {
       mbar_arrive_expect_tx(bfull, kBBytes);
 #pragma unroll
-      for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_b + bx * (kBN * 128), &tm_b, bfull, bx * 64, (t0 + nis) * kBN);
+      for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_b + bx * (kBN * 128), &tm_b, bfull, bx * 64, (t0 + n) * kBN);
     }
-    ++nis;
+    __syncwarp();
   };
-  auto issue_mma = [&]() {
+  auto step1 = [&]() {
     tc_fence_after();
     if (elect_one()) {
+      const int slot = m_next % kTBufs;
+      mbar_arrive_expect_tx(&lfull[slot], kLStage);
+      uint8_t* dst = s_l + (size_t)slot * kLStage;
+      const int ta = t0 + m_next;
+      bulk_load(dst, p.lfix + (size_t)ta * PtPad * 64, kLBytes, &lfull[slot]);
+      bulk_load(dst + kLBytes, p.d + (size_t)ta * 64, kBN * 4, &lfull[slot]);
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
       const uint64_t ad0 = umma_desc_sw128(smem_u32(s_a), 0, 1024), bd0 = umma_desc_sw128(smem_u32(s_b), 0, 1024);
-      const uint32_t tacc = tmem_base + (nis % kTBufs) * kBN;
+      const uint32_t tacc = tmem_base + slot * kBN;
 #pragma unroll
       for (int k = 0; k < kD / 16; ++k)      // descriptor start addresses advance in 16-byte units
         umma_f16(tacc, ad0 + (uint64_t)(((k >> 2) * (kBM * 128) + (k & 3) * 32) >> 4),
                  bd0 + (uint64_t)(((k >> 2) * (kBN * 128) + (k & 3) * 32) >> 4), idesc, k != 0);
       umma_commit(bempty);
-      umma_commit(&tfull[nis % kTBufs]);
+      umma_commit(&tfull[slot]);
+      *s_mcnt = m_next + 1;
     }
-    ++nis;
-  };
-  // non-blocking: issue the next item of this warp's role if its gate is open (every lane probes, so the answer
-  // and with it nis stay warp-uniform)
-  auto poll = [&]() {
-    if (nis >= ntiles) return;
-    bool open;
-    if (role_l) open = mbar_test(&lempty[nis % kLStages], ((nis / kLStages) & 1) ^ 1);
-    else if (role_b) open = mbar_test(bempty, (nis & 1) ^ 1);
-    else open = mbar_test(bfull, nis & 1) && mbar_test(&tempty[nis % kTBufs], ((nis / kTBufs) & 1) ^ 1);
-    if (__all_sync(0xffffffffu, open)) {
-      if (role_l) issue_l(); else if (role_b) issue_b(); else issue_mma();
-    }
+    b_pend = (m_next + 1 < ntiles) ? m_next : -1;
+    m_next += kSwWarps;
     __syncwarp();
   };
-  // blocking: the item tile `it` needs has been issued (its gates only depend on strictly older tiles)
-  auto ensure = [&](int it) {
-    while (nis <= it) {
-      if (role_l) { mbar_wait_idle(&lempty[nis % kLStages], ((nis / kLStages) & 1) ^ 1, 2000u); __syncwarp(); issue_l(); }
-      else if (role_b) { mbar_wait_idle(bempty, (nis & 1) ^ 1, 2000u); __syncwarp(); issue_b(); }
-      else {
-        mbar_wait_idle(bfull, nis & 1, 2000u);
-        mbar_wait_idle(&tempty[nis % kTBufs], ((nis / kTBufs) & 1) ^ 1, 2000u);
-        __syncwarp();
-        issue_mma();
-      }
-      __syncwarp();
+  // non-blocking (every lane probes and the vote keeps the answer, and with it m_next / b_pend, warp-uniform)
+  auto poll = [&](int it) {
+    if (b_pend >= 0) {
+      if (__all_sync(0xffffffffu, mbar_test(bempty, b_pend & 1))) { issue_b(b_pend + 1); b_pend = -1; }
+    } else if (m_next < ntiles && m_next - it <= kTBufs) {      // its ring slot can be free at the earliest now
+      const uint32_t par = ((m_next / kTBufs) & 1) ^ 1;
+      const bool open = (*s_mcnt == m_next) && mbar_test(bfull, m_next & 1) && mbar_test(&tempty[m_next % kTBufs], par) &&
+                        mbar_test(&lempty[m_next % kTBufs], par);
+      if (__all_sync(0xffffffffu, open)) step1();
     }
   };
-  const bool driver = role_l || role_b || role_m;
-  if (role_m) {
+  // blocking: everything tile `it` needs from this warp has been issued.  The gates only depend on strictly
+  // older tiles, which every warp that reached `it` has passed, and on steps their owners complete here.
+  auto ensure = [&](int it) {
+    if (b_pend >= 0 && b_pend < it) {
+      mbar_wait_idle(bempty, b_pend & 1, 2000u);
+      __syncwarp();
+      issue_b(b_pend + 1);
+      b_pend = -1;
+    }
+    if (m_next <= it) {
+      const uint32_t par = ((m_next / kTBufs) & 1) ^ 1;
+      while (*s_mcnt != m_next) {}
+      mbar_wait_idle(bfull, m_next & 1, 2000u);
+      mbar_wait_idle(&tempty[m_next % kTBufs], par, 2000u);
+      mbar_wait_idle(&lempty[m_next % kTBufs], par, 2000u);
+      __syncwarp();
+      step1();
+    }
+  };
+  if (warp == 0) {
     if (elect_one()) {
       mbar_arrive_expect_tx(afull, kABytes);
 #pragma unroll
       for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_a + bx * (kBM * 128), &tm_a, afull, bx * 64, i0);
     }
     __syncwarp();
-    mbar_wait(afull, 0);
+    issue_b(0);
   }
+  mbar_wait(afull, 0);                                   // every warp issues MMAs that read the A tile
 
   const int q = warp & 3, hc = warp >> 2;
   const int tid = threadIdx.x;                         // = hc*128 + row in block
@@ -656,11 +661,12 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
 #ifdef IMP_SWEEP_TRACE
     const long long c0t = clock64();
 #endif
-    if (driver) { ensure(it); poll(); }
+    ensure(it);
+    poll(it);
     __syncwarp();
 #ifdef IMP_SWEEP_TRACE
     const long long c1t = clock64();
-    tr_look += driver ? nis - it : 0;
+    tr_look += *s_mcnt - it;
 #endif
     // suspended waits: a warp that ran ahead must not spin away the issue slots of the warps it is waiting for
     mbar_wait_idle(&tfull[tb], (it / kTBufs) & 1, 4000u);
@@ -748,7 +754,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[tb]);
         }
-        if (driver) poll();
+        poll(it);
         __syncwarp();
       }
     };
