@@ -771,7 +771,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
       }
     };
     auto tile = [&](auto interior_tag) {
-#pragma unroll
+#pragma unroll 2      // not 4: the fully unrolled tile (21 KB of SASS per variant) stalled on instruction fetch (37.6 -> 35.8 ms); 1 is slower (38.6)
       for (int g = 0; g < 4; ++g) {
         group4(g, interior_tag);
         if (g == 3) {                                    // the accumulator buffer has been read completely
