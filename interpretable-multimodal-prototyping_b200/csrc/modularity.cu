@@ -509,11 +509,9 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_dm + 16);
   uint64_t* bfull = bars;                 // TMA -> MMA
   uint64_t* bempty = bars + 1;            // MMA commit -> TMA
-  uint64_t* tfull = bars + 2;             // [kTBufs] MMA -> sweep
-  uint64_t* tempty = tfull + kTBufs;      // [kTBufs] 16 warps -> MMA
-  uint64_t* lfull = tempty + kTBufs;      // [kLStages] bulk copy -> sweep
-  uint64_t* lempty = lfull + kLStages;    // [kLStages] 16 warps -> bulk copy
-  uint64_t* afull = lempty + kLStages;
+  uint64_t* full = bars + 2;              // [kTBufs] ring slot filled: L/degree bytes landed AND the MMAs retired
+  uint64_t* empty = full + kTBufs;        // [kTBufs] ring slot consumed by all 16 warps
+  uint64_t* afull = empty + kTBufs;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
   float* s_red = reinterpret_cast<float*>(tmem_slot + 2);                 // [16][2]
   volatile int* s_mcnt = reinterpret_cast<volatile int*>(s_red + 2 * kSwWarps);
@@ -533,8 +531,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     mbar_init(bfull, 1); mbar_init(bempty, 1);
-    for (int i = 0; i < kTBufs; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kSwWarps); }
-    for (int i = 0; i < kLStages; ++i) { mbar_init(&lfull[i], 1); mbar_init(&lempty[i], kSwWarps); }
+    for (int i = 0; i < kTBufs; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], kSwWarps); }   // 2 = expect_tx arrive + commit
     mbar_init(afull, 1);
     *s_mcnt = 0;
     mbar_fence_init();
@@ -547,7 +544,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   // Producer work rotates over the 16 warps: warp n % 16 owns tile n and, from inside its own sweep, at non-blocking
   // probe points (five per tile), performs
   //   step 1 (gates: tiles < n issued, B box n landed, ring slot n % 4 released by all 16 warps):
-  //           bulk copies of the L / degree tile n, the 16 tcgen05 MMAs of tile n, commits to bempty and tfull;
+  //           bulk copies of the L / degree tile n, the 16 tcgen05 MMAs of tile n, commits to bempty and full;
   //   step 2 (gate: the MMAs of tile n have retired = bempty): TMA load of B box n + 1 (single stage).
   // Every step runs on a whole, converged warp and the asynchronous instructions on the lane elect.sync picks:
   // inside an elect-guarded block ptxas keeps descriptors and barrier addresses in uniform registers (~45
@@ -571,11 +568,11 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     tc_fence_after();
     if (elect_one()) {
       const int slot = m_next % kTBufs;
-      mbar_arrive_expect_tx(&lfull[slot], kLStage);
+      mbar_arrive_expect_tx(&full[slot], kLStage);
       uint8_t* dst = s_l + (size_t)slot * kLStage;
       const int ta = t0 + m_next;
-      bulk_load(dst, p.lfix + (size_t)ta * PtPad * 64, kLBytes, &lfull[slot]);
-      bulk_load(dst + kLBytes, p.d + (size_t)ta * 64, kBN * 4, &lfull[slot]);
+      bulk_load(dst, p.lfix + (size_t)ta * PtPad * 64, kLBytes, &full[slot]);
+      bulk_load(dst + kLBytes, p.d + (size_t)ta * 64, kBN * 4, &full[slot]);
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
       const uint64_t ad0 = umma_desc_sw128(smem_u32(s_a), 0, 1024), bd0 = umma_desc_sw128(smem_u32(s_b), 0, 1024);
       const uint32_t tacc = tmem_base + slot * kBN;
@@ -584,7 +581,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
         umma_f16(tacc, ad0 + (uint64_t)(((k >> 2) * (kBM * 128) + (k & 3) * 32) >> 4),
                  bd0 + (uint64_t)(((k >> 2) * (kBN * 128) + (k & 3) * 32) >> 4), idesc, k != 0);
       umma_commit(bempty);
-      umma_commit(&tfull[slot]);
+      umma_commit(&full[slot]);
       *s_mcnt = m_next + 1;
     }
     b_pend = (m_next + 1 < ntiles) ? m_next : -1;
@@ -597,8 +594,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
       if (__all_sync(0xffffffffu, mbar_test(bempty, b_pend & 1))) { issue_b(b_pend + 1); b_pend = -1; }
     } else if (m_next < ntiles && m_next - it <= kTBufs) {      // its ring slot can be free at the earliest now
       const uint32_t par = ((m_next / kTBufs) & 1) ^ 1;
-      const bool open = (*s_mcnt == m_next) && mbar_test(bfull, m_next & 1) && mbar_test(&tempty[m_next % kTBufs], par) &&
-                        mbar_test(&lempty[m_next % kTBufs], par);
+      const bool open = (*s_mcnt == m_next) && mbar_test(bfull, m_next & 1) && mbar_test(&empty[m_next % kTBufs], par);
       if (__all_sync(0xffffffffu, open)) step1();
     }
   };
@@ -615,8 +611,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
       const uint32_t par = ((m_next / kTBufs) & 1) ^ 1;
       while (*s_mcnt != m_next) {}
       mbar_wait_idle(bfull, m_next & 1, 2000u);
-      mbar_wait_idle(&tempty[m_next % kTBufs], par, 2000u);
-      mbar_wait_idle(&lempty[m_next % kTBufs], par, 2000u);
+      mbar_wait_idle(&empty[m_next % kTBufs], par, 2000u);
       __syncwarp();
       step1();
     }
@@ -695,12 +690,11 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
 #endif
     // sleeping waits: a warp that ran ahead must not spin away the issue slots of the warps it is waiting for
     // (try_wait with a suspend hint still came back every ~6 cycles here: 8% of all issued instructions)
-    mbar_wait_sleep(&tfull[tb], (it / kTBufs) & 1);
+    mbar_wait_sleep(&full[tb], (it / kTBufs) & 1);
     tc_fence_after();
 #ifdef IMP_SWEEP_TRACE
     const long long c2t = clock64();
 #endif
-    mbar_wait_sleep(&lfull[ls], (it / kLStages) & 1);
 #ifdef IMP_SWEEP_TRACE
     const long long c3t = clock64();
     tr_e += c1t - c0t; tr_t += c2t - c1t; tr_l += c3t - c2t;
@@ -774,18 +768,14 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
 #pragma unroll 2      // not 4: the fully unrolled tile (21 KB of SASS per variant) stalled on instruction fetch (37.6 -> 35.8 ms); 1 is slower (38.6)
       for (int g = 0; g < 4; ++g) {
         group4(g, interior_tag);
-        if (g == 3) {                                    // the accumulator buffer has been read completely
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[tb]);
-        }
         poll(it);
         __syncwarp();
       }
     };
     if (interior) tile(std::true_type{}); else tile(std::false_type{});
+    tc_fence_before();                                   // accumulator and L tile of the slot have been read completely
     __syncwarp();
-    if (lane == 0) mbar_arrive(&lempty[ls]);
+    if (lane == 0) mbar_arrive(&empty[tb]);
   }
 #ifdef IMP_SWEEP_TRACE
   if (lane == 0) {     // per warp: cycles waiting for the accumulator / the L tile / inside ensure(), loop cycles, tiles, look-ahead
