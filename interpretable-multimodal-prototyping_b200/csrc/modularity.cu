@@ -515,6 +515,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
   float* s_red = reinterpret_cast<float*>(tmem_slot + 2);                 // [16][2]
   volatile int* s_mcnt = reinterpret_cast<volatile int*>(s_red + 2 * kSwWarps);
+  volatile uint64_t* s_desc = reinterpret_cast<volatile uint64_t*>(s_red + 2 * kSwWarps + 2);   // UMMA descriptors of A and B
 
   const int b = blockIdx.z;
   const int row_begin = __ldg(p.cu + b), row_end = __ldg(p.cu + b + 1);
@@ -534,6 +535,8 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     for (int i = 0; i < kTBufs; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], kSwWarps); }   // 2 = expect_tx arrive + commit
     mbar_init(afull, 1);
     *s_mcnt = 0;
+    s_desc[0] = umma_desc_sw128(smem_u32(s_a), 0, 1024);
+    s_desc[1] = umma_desc_sw128(smem_u32(s_b), 0, 1024);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, kTBufs * kBN);
@@ -574,7 +577,9 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
       bulk_load(dst, p.lfix + (size_t)ta * PtPad * 64, kLBytes, &full[slot]);
       bulk_load(dst + kLBytes, p.d + (size_t)ta * 64, kBN * 4, &full[slot]);
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
-      const uint64_t ad0 = umma_desc_sw128(smem_u32(s_a), 0, 1024), bd0 = umma_desc_sw128(smem_u32(s_b), 0, 1024);
+      // base descriptors come from shared memory: computed here from the (loop-invariant) buffer addresses, ptxas
+      // hoists the 32 additions below out of this block into every warp's tile loop (~40 instructions per tile)
+      const uint64_t ad0 = s_desc[0], bd0 = s_desc[1];
       const uint32_t tacc = tmem_base + slot * kBN;
 #pragma unroll
       for (int k = 0; k < kD / 16; ++k)      // descriptor start addresses advance in 16-byte units
