@@ -1,4 +1,4 @@
-// temporary microbenchmark: shared-memory integer atomic add (no return) vs LDS+FADD+STS, per warp instruction
+// microbenchmark (nvcc -gencode arch=compute_100a,code=sm_100a -O3; results in profiles/r01_microbench.md): shared-memory integer atomic add (no return) vs LDS+FADD+STS, per warp instruction
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>

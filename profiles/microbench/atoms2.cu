@@ -1,4 +1,4 @@
-// temporary microbenchmark: shared int atomics with k distinct addresses per warp instruction (same-address collisions)
+// microbenchmark (nvcc -gencode arch=compute_100a,code=sm_100a -O3; results in profiles/r01_microbench.md): shared int atomics with k distinct addresses per warp instruction (same-address collisions)
 #include <cstdio>
 #include <cuda_runtime.h>
 __global__ void k(int* out, int iters, long long* cyc, int distinct, int stride) {

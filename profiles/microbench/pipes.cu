@@ -1,4 +1,4 @@
-// temporary microbenchmark: issue rate per SM sub-partition of the sweep's main instructions (4 warps / SMSP, 8 chains)
+// microbenchmark (nvcc -gencode arch=compute_100a,code=sm_100a -O3; results in profiles/r01_microbench.md): issue rate per SM sub-partition of the sweep's main instructions (4 warps / SMSP, 8 chains)
 #include <cstdio>
 #include <cuda_runtime.h>
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {

@@ -1,4 +1,5 @@
-"""temporary: per-warp wait counters of the sweep kernel (build with IMP_NVCC_EXTRA=-DIMP_SWEEP_TRACE)."""
+"""Per-warp wait counters of the modularity sweep (profiles/r01_sweep_iterations.md).
+Build the library with  IMP_NVCC_EXTRA=-DIMP_SWEEP_TRACE python interpretable-multimodal-prototyping_b200/build.py  first."""
 import ctypes, sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
