@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bags", type=int, default=32, help="slides per step per GPU")
-    ap.add_argument("--e2e-bags", type=int, default=16, help="slides per step of the host-buffer (e2e) leg")
+    ap.add_argument("--e2e-bags", type=int, default=32, help="slides per step of the host-buffer (e2e) leg")
     ap.add_argument("--patches", type=int, default=N_PATCH)
     ap.add_argument("--protos", type=int, default=N_PROTO)
     ap.add_argument("--no-cpu-baseline", action="store_true")
