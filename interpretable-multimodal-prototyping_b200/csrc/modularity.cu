@@ -89,6 +89,17 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   while (!mbar_test(bar, parity)) __nanosleep(40);
 }
+// T[slot] += v on the token-major fixed-point array (row stride 512 B): one IMAD for the address (the compiler's
+// own form is shift + mask + add) and a fire-and-forget ATOMS.ADD
+__device__ __forceinline__ void red_shared_add(uint32_t base, int slot, int v) {
+  asm volatile(
+      "{\n\t"
+      ".reg .u32 a;\n\t"
+      "mad.lo.u32 a, %1, 512, %0;\n\t"
+      "red.shared.add.s32 [a], %2;\n\t"
+      "}" ::"r"(base), "r"(slot), "r"(v)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -490,7 +501,7 @@ constexpr size_t sweep_smem() {
   return 1024 + kABytes + kBBytes + (size_t)kLStages * (kBN * PtPad * 4 + kBN * 4) + (size_t)PtPad * kBM * 4 + kBM * 4 + 64 + 512;
 }
 
-template <int NQ1, int NQ2>
+template <int NQ1, int NQ2, bool LASTPAD>      // LASTPAD: the last token slot is padding (never wins): skipped
 __global__ void __launch_bounds__(kSwThreads, 1)
 modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                         const GramParams p) {
@@ -636,7 +647,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   const int tid = threadIdx.x;                         // = hc*128 + row in block
   const int i = i0 + q * 32 + lane;
   const bool row_ok = i < own_end;
-  int* myT = s_T + q * 32 + lane;                      // element p of this thread's row at myT[p * 128]
+  const uint32_t myT_s = smem_u32(s_T + q * 32 + lane);   // element p of this thread's row at byte offset p * 512
   float Li[PtPad];                                     // row operand: 2^23 + (N_i << 5)
 #pragma unroll
   for (int k = 0; k < PtPad; ++k) {
@@ -724,9 +735,17 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
         constexpr int dummy = 0; (void)dummy;
         const int grp = (2 * pp >= 4 * NQ1) ? 1 : 0;
         const float4 w0 = sL[(2 * pp) * 16 + g];
-        const float4 w1 = sL[(2 * pp + 1) * 16 + g];
-        const float2 la = make_float2(Li[2 * pp], Li[2 * pp]), lb = make_float2(Li[2 * pp + 1], Li[2 * pp + 1]);
+        const float2 la = make_float2(Li[2 * pp], Li[2 * pp]);
         const float2 a01 = add2(make_float2(w0.x, w0.y), la), a23 = add2(make_float2(w0.z, w0.w), la);
+        if (LASTPAD && pp == PtPad / 2 - 1) {             // slot PtPad-1 holds the padding value for every row and column
+          m[0][grp] = fminf(a01.x, m[0][grp]);
+          m[1][grp] = fminf(a01.y, m[1][grp]);
+          m[2][grp] = fminf(a23.x, m[2][grp]);
+          m[3][grp] = fminf(a23.y, m[3][grp]);
+          continue;
+        }
+        const float4 w1 = sL[(2 * pp + 1) * 16 + g];
+        const float2 lb = make_float2(Li[2 * pp + 1], Li[2 * pp + 1]);
         const float2 b01 = add2(make_float2(w1.x, w1.y), lb), b23 = add2(make_float2(w1.z, w1.w), lb);
         m[0][grp] = fminf(fminf(a01.x, b01.x), m[0][grp]);
         m[1][grp] = fminf(fminf(a01.y, b01.y), m[1][grp]);
@@ -764,8 +783,8 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
           sg[grp] = fma2(gw, delta, sg[grp]);                           // sum of S gs4 * (A/e - d_i d_j/e^2) * delta
           // t = 2 g (1-delta^2)/temp * u, 1-delta^2 = 4 e2 r^2, times S, rounded to an integer by the magic addend
           const float2 tf = fma2(mul2(gw, t1), mul2(r, u), magic2);
-          atomicAdd(myT + (pl0 + (grp ? 4 * NQ1 : 0)) * kBM, __float_as_int(tf.x) - 0x4B400000);
-          atomicAdd(myT + (pl1 + (grp ? 4 * NQ1 : 0)) * kBM, __float_as_int(tf.y) - 0x4B400000);
+          red_shared_add(myT_s + (grp ? 4 * NQ1 * kBM * 4 : 0), pl0, __float_as_int(tf.x) - 0x4B400000);
+          red_shared_add(myT_s + (grp ? 4 * NQ1 * kBM * 4 : 0), pl1, __float_as_int(tf.y) - 0x4B400000);
         }
       }
     };
@@ -1020,16 +1039,16 @@ int run_degrees(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& 
   return IMP_OK;
 }
 
-template <int NQ1, int NQ2>
+template <int NQ1, int NQ2, bool LASTPAD = false>
 int run_sweep(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p, dim3 grid, cudaStream_t st) {
   constexpr size_t smem = sweep_smem<NQ1, NQ2>();
   static_assert(smem <= 227 * 1024, "modularity_sweep shared memory");
   static bool done = false;
   if (!done) {
-    IMP_CUDA(cudaFuncSetAttribute(modularity_sweep_kernel<NQ1, NQ2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IMP_CUDA(cudaFuncSetAttribute(modularity_sweep_kernel<NQ1, NQ2, LASTPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done = true;
   }
-  IMP_LAUNCH("modularity_sweep", st, modularity_sweep_kernel<NQ1, NQ2><<<grid, kSwThreads, smem, st>>>(ta, tb, p));
+  IMP_LAUNCH("modularity_sweep", st, modularity_sweep_kernel<NQ1, NQ2, LASTPAD><<<grid, kSwThreads, smem, st>>>(ta, tb, p));
   return IMP_OK;
 }
 
@@ -1178,6 +1197,7 @@ int launch_modularity_execute(const bf16* h_local, int local_rows, int row_lo, i
     const dim3 grid(row_blocks, nsplit, B);
 #define IMP_SWEEP(a, b2) rc = run_sweep<a, b2>(ta, tb, gp, grid, st)
     if (nq2 == 0) { if (nq1 == 2) IMP_SWEEP(2, 0); else if (nq1 == 4) IMP_SWEEP(4, 0); else IMP_SWEEP(8, 0); }
+    else if (nq1 == 8 && (P2 & 3)) rc = run_sweep<8, 2, true>(ta, tb, gp, grid, st);     // the 32 + 7 token configuration
     else { if (nq1 == 2) IMP_SWEEP(2, 2); else if (nq1 == 4) IMP_SWEEP(4, 2); else IMP_SWEEP(8, 2); }
 #undef IMP_SWEEP
     if (rc) return rc;
