@@ -31,7 +31,7 @@ GROUP_SIZES = [82, 330, 513, 440, 1538, 451]
 WORKLOAD = "configs[1]: survival training, synthetic TCGA-shaped bags 16384x512, 32 prototypes, 6 pathways, bf16"
 # dram__bytes_read.sum + dram__bytes_write.sum of one modularity_sweep launch from `ncu --set full`
 # (profiles/r01_ncu_full_final.md), keyed by bags per launch; None when not captured for that size
-SWEEP_TRAFFIC_PER_LAUNCH = {32: 423.7e6 + 61.3e6}
+SWEEP_TRAFFIC_PER_LAUNCH = {32: 423.1e6 + 62.2e6}
 # the same sum over one step's launches of the streaming kernels (path_net fwd, 2x pool fwd + merge, 2x dq, dz, dW1)
 STREAM_TRAFFIC_PER_STEP = {32: 3.26e9}
 
@@ -336,11 +336,11 @@ def run_ours(args):
         roofline["cuda_core_issue"] = {
             "pairs_per_s": pairs / t, "token_pair_evals_per_s": pairs * (P + N_PATHWAYS + 1) / t,
             "sm_cycles_per_32_pairs": t * clk * 1e6 * sm_count * 4 / (pairs / 32),
-            "warp_instructions_per_32_pairs": 90, "alu_pipe_cycles_per_32_pairs": 94,
-            "what": "cycles of one scheduler sub-partition per warp of 32 pairs; 90 instructions at 1 IPC would be the "
-            "issue bound, 94 cycles the ALU-pipe bound (20 FMNMX3 at 3.7 cycles + 10 other ALU instructions at 2, "
+            "warp_instructions_per_32_pairs": 87, "alu_pipe_cycles_per_32_pairs": 92,
+            "what": "cycles of one scheduler sub-partition per warp of 32 pairs; 87 instructions at 1 IPC would be the "
+            "issue bound, 92 cycles the ALU-pipe bound (19.5 FMNMX3 at 3.7 cycles + 10 other ALU instructions at 2, "
             "measured pipe rates in profiles/r01_sweep_iterations.md)"}
-        roofline["cuda_core_issue"]["frac_of_alu_pipe_bound"] = round(94.0 / roofline["cuda_core_issue"]["sm_cycles_per_32_pairs"], 4)
+        roofline["cuda_core_issue"]["frac_of_alu_pipe_bound"] = round(92.0 / roofline["cuda_core_issue"]["sm_cycles_per_32_pairs"], 4)
         roofline["traffic"] = SWEEP_TRAFFIC_PER_LAUNCH.get(B)
     # fused streaming path (the metric's 'fused-kernel HBM GB/s'): x read once forward + once backward
     stream_names = ["pathnet_fwd", "pool_fwd", "pool_merge", "pool_bwd_dq", "pool_bwd_dz", "reduce_dq", "reduce_db", "pathnet_dw",

@@ -24,7 +24,7 @@ def _inputs(n, p, q, seed):
     return h, c1, c2
 
 
-@pytest.mark.parametrize("n,p,q", [(128, 6, 0), (300, 16, 7), (1000, 6, 7), (2048, 32, 7), (4096 + 77, 32, 0)])
+@pytest.mark.parametrize("n,p,q", [(128, 6, 0), (300, 16, 7), (1000, 6, 7), (2048, 32, 7), (640, 32, 8), (4096 + 77, 32, 0)])
 def test_modularity_vs_oracle(n, p, q):
     from imp_b200 import modularity as M
     from oracle import imp_oracle as O
