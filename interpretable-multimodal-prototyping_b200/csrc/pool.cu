@@ -708,16 +708,29 @@ constexpr size_t bwd_smem() {
   return 1024 + (size_t)STAGES * kTileBytes + 2 * NB * PP * 512 + e + 2 * NB * PP * 4 + 2 * STAGES * 8 + 64;
 }
 
-void split_plan(int max_len, int B, int* nsplit, int* tiles_per_split) {
+// Split every bag into `nsplit` runs of `tiles_per_split` tiles so that the B * nsplit CTAs fill whole waves of
+// the `slots` CTAs the GPU holds at once: cost = waves * (tiles per CTA + 1 tile-equivalent of prologue).  Rounding
+// the split count up to "at least two waves" (the first version) gave 608 CTAs on 296 slots for 32 bags: a third
+// wave of 16 CTAs, 1.5x the time of two full waves.
+void best_split(int tiles, int B, int slots, int min_tiles, int max_split, int* nsplit, int* tiles_per_split) {
+  const int cap = max(1, min(tiles / max(1, min_tiles), max_split));
+  long best_cost = -1;
+  int best_ns = 1, best_tps = tiles;
+  for (int ns = 1; ns <= cap; ++ns) {
+    const int tps = (tiles + ns - 1) / ns;
+    const int real_ns = (tiles + tps - 1) / tps;
+    const long waves = ((long)B * real_ns + slots - 1) / slots;
+    const long cost = waves * (tps + 1);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_ns = real_ns; best_tps = tps; }
+  }
+  *nsplit = best_ns;
+  *tiles_per_split = best_tps;
+}
+
+// forward / dq: 64-row tiles, two CTAs resident per SM up to 32 prototypes (one above), at least 8 tiles (256 KB of h) per CTA
+void split_plan(int max_len, int B, int P, int* nsplit, int* tiles_per_split) {
   const int tiles = max(1, (max_len + kTM - 1) / kTM);
-  const int sms = imp_num_sms();
-  // aim for >= 2 waves of CTAs (two resident per SM) while keeping at least 8 tiles (256 KB of h) per CTA
-  int want = max(1, (4 * sms + B - 1) / B);
-  int cap = max(1, tiles / 8);
-  int ns = min(want, cap);
-  ns = min(ns, 256);
-  *tiles_per_split = (tiles + ns - 1) / ns;
-  *nsplit = (tiles + *tiles_per_split - 1) / *tiles_per_split;
+  best_split(tiles, B, (P <= 32 ? 2 : 1) * imp_num_sms(), 8, 256, nsplit, tiles_per_split);
 }
 
 template <int PP, int STAGES>
@@ -757,12 +770,10 @@ int run_dz(const CUtensorMap& tm, const DzParams& p, int B, cudaStream_t st) {
   return IMP_OK;
 }
 
-// 128-row tiles, one CTA per SM: >= 2 waves of CTAs, at least 4 tiles (256 KB of h) per CTA
+// dz: 128-row tiles, one CTA per SM, at least 4 tiles (256 KB of h) per CTA
 void dz_split_plan(int max_len, int B, int* nsplit, int* tiles_per_split) {
   const int tiles = max(1, (max_len + kZM - 1) / kZM);
-  int ns = max(1, min(min((2 * imp_num_sms() + B - 1) / B, max(1, tiles / 4)), 128));
-  *tiles_per_split = (tiles + ns - 1) / ns;
-  *nsplit = (tiles + *tiles_per_split - 1) / *tiles_per_split;
+  best_split(tiles, B, imp_num_sms(), 4, 128, nsplit, tiles_per_split);
 }
 
 }  // namespace
@@ -772,7 +783,7 @@ void dz_split_plan(int max_len, int B, int* nsplit, int* tiles_per_split) {
 // ------------------------------------------------------------------------------------------
 size_t pool_fwd_workspace_bytes(int B, int max_len, int P) {
   int ns, tps;
-  split_plan(max_len, B, &ns, &tps);
+  split_plan(max_len, B, P, &ns, &tps);
   const int PP = pad_protos(P);
   return ((size_t)B * ns * PP * kD + (size_t)B * ns * 2 * PP) * sizeof(float);
 }
@@ -784,7 +795,7 @@ int launch_pool_fwd(const bf16* h, int total_rows, const int* cu, int B, int max
   if (total_rows <= 0 || max_len <= 0) IMP_FAIL(IMP_ERR_ARG, "pool_fwd: empty input (rows=%d, max_len=%d)", total_rows, max_len);
   const int PP = pad_protos(P);
   PoolFwdParams p;
-  split_plan(max_len, B, &p.nsplit, &p.tiles_per_split);
+  split_plan(max_len, B, P, &p.nsplit, &p.tiles_per_split);
   p.cu = cu; p.qt = qt; p.qt_stride = qt_stride; p.P = P;
   p.part_acc = workspace;
   p.part_ml = workspace + (size_t)B * p.nsplit * PP * kD;
@@ -802,7 +813,7 @@ int launch_pool_fwd(const bf16* h, int total_rows, const int* cu, int B, int max
 
 size_t pool_bwd_workspace_bytes(int B, int max_len, int P) {
   int ns, tps;
-  split_plan(max_len, B, &ns, &tps);
+  split_plan(max_len, B, P, &ns, &tps);
   const int PP = pad_protos(P);
   int nz, tz;
   dz_split_plan(max_len, B, &nz, &tz);
@@ -821,7 +832,7 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
   if (nblocks == 2 && P > 32) IMP_FAIL(IMP_ERR_ARG, "pool_bwd: two stacked blocks need P <= 32 (got %d)", P);
   const int PP = pad_protos(P);
   PoolBwdParams p;
-  split_plan(max_len, B, &p.nsplit, &p.tiles_per_split);
+  split_plan(max_len, B, P, &p.nsplit, &p.tiles_per_split);
   p.cu = cu; p.P = P; p.dq_block = dq_block;
   for (int k = 0; k < 2; ++k) {
     const int s = k < nblocks ? k : 0;
