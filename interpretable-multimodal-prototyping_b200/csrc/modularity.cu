@@ -1216,7 +1216,17 @@ int launch_modularity_execute(const bf16* h_local, int local_rows, int row_lo, i
   if ((rc = imp_make_tmap_2d(&th, h_local, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, (uint64_t)std::max(local_rows, 1), kD * 2, 64, kBN,
                              CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   const int fin_tiles = (std::max(own_len, 1) + 63) / 64 + 1;
-  const int fin_chunks = std::max(1, std::min(fin_tiles, (imp_num_sms() + B - 1) / B));
+  // one CTA per SM (218 KB of shared memory): chunks per bag that fill whole waves, cost = waves * (tiles per CTA + 2)
+  // (rounding up to ceil(SMs / B) chunks gave 160 CTAs on 148 SMs for 32 bags: a second wave of 12)
+  int fin_chunks = 1;
+  {
+    long best = -1;
+    for (int ch = 1; ch <= std::min(fin_tiles, 2 * imp_num_sms()); ++ch) {
+      const int tps = (fin_tiles + ch - 1) / ch, real = (fin_tiles + tps - 1) / tps;
+      const long cost = (((long)B * real + imp_num_sms() - 1) / imp_num_sms()) * (tps + 2);
+      if (best < 0 || cost < best) { best = cost; fin_chunks = real; }
+    }
+  }
   fp.rows_per_cta = (fin_tiles + fin_chunks - 1) / fin_chunks;           // tiles per CTA
   const dim3 fgrid((fin_tiles + fp.rows_per_cta - 1) / fp.rows_per_cta, B);
 #define IMP_FIN(PT)                                                                                                    \
