@@ -673,7 +673,8 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   __syncthreads();
 #pragma unroll
   for (int w = 0; w < kSwWarps; ++w) dmax = fmaxf(dmax, s_dm[w]);
-  float sraw = 1073741824.f / ((float)(ntiles * kBN) * 92.f * fmaxf(k1, k2 * di * dmax));
+  // at least 512 columns in the denominator: a single term stays below 2^21, inside the range of the magic-number rounding
+  float sraw = 1073741824.f / ((float)max(ntiles * kBN, 512) * 92.f * fmaxf(k1, k2 * di * dmax));
   if (!(sraw < 1e30f)) sraw = 1e30f;
   if (!(sraw > 1e-30f)) sraw = 1e-30f;
   const float S = __int_as_float(__float_as_int(sraw) & 0x7f800000);     // 2^floor(log2 sraw)

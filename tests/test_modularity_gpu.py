@@ -152,3 +152,31 @@ def test_modularity_fixed_point_accumulation_on_skewed_degrees(temp):
     ref, dref = O.modularity(c1, h.float(), temp=temp, chunk=256)
     assert abs(loss[0, 0].item() - ref.item()) <= 1e-3 * abs(ref.item()) + ABS_TOL, (loss[0, 0].item(), ref.item())
     assert rel(c1d.grad[0], dref) < 1e-2, rel(c1d.grad[0], dref)
+
+
+def test_modularity_three_edge_graph_near_the_fixed_point_bound():
+    """125 mutually orthogonal patches, one identical pair and one patch at 45 degrees to it: a graph with three
+    edges (d = 0 for 125 rows, e = 4.8) whose pair has A = 1 and u = max_p C_ip C_jp = 0.077 = 0.77 temp, the maximum
+    of u / cosh^2(u / temp): |t_ij| comes within a factor of a few of the bound the fixed-point scale of T is derived
+    from, in a CTA with only two column tiles (the scale is capped so that a single term stays inside the
+    magic-number range), and most rows have a zero degree."""
+    from imp_b200 import modularity as M
+    from oracle import imp_oracle as O
+    n, p = 128, 13
+    h = torch.zeros(n, 256)
+    h[torch.arange(126), torch.arange(126)] = 1.0
+    h[126, 126] = 1.0
+    h[127, 126] = 1.0
+    h[125, 126] = 1.0                                 # a third patch at 45 degrees: without it the two traces cancel exactly
+    g = torch.Generator().manual_seed(3)
+    c1 = 0.01 * torch.rand(p, 256, generator=g) + 0.01
+    c1[:, 126] = 1.0                                  # equal over tokens: C_ip = 1/sqrt(13) for the pair, every p
+    cu = torch.tensor([0, n], dtype=torch.int32, device="cuda")
+    c1d = c1.cuda().unsqueeze(0).requires_grad_(True)
+    loss = M.modularity_terms(h.bfloat16().cuda(), cu, n, c1d, None)
+    loss[0, 0].backward()
+    torch.cuda.synchronize()
+    ref, dref = O.modularity(c1, h, chunk=128)
+    assert abs(loss[0, 0].item() - ref.item()) <= 1e-3 * abs(ref.item()) + ABS_TOL, (loss[0, 0].item(), ref.item())
+    assert torch.isfinite(c1d.grad).all()
+    assert rel(c1d.grad[0], dref) < 2e-3, rel(c1d.grad[0], dref)
