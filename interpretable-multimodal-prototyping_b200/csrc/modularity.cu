@@ -478,8 +478,8 @@ modularity_degrees_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
 //   the 64 columns, four at a time), 128 registers per thread (a 17th warp would cap every thread at 96).
 //   No dedicated producer / MMA warps: the pair work of a tile takes microseconds, so the sweep warps drive the
 //   asynchronous machinery themselves, in rotation, with non-blocking mbarrier probes (five probe points per
-//   tile): bulk copies of the L/degree tiles and the tcgen05 MMA 128x64x256 into a ring of four slots (TMEM
-//   accumulator + L tile), up to three tiles ahead, and the TMA load of the B box (1 stage: it is free again as
+//   tile): bulk copies of the L/degree tiles and the tcgen05 MMA 128x64x256 into a ring of eight slots (TMEM
+//   accumulator + L tile: all 512 TMEM columns), up to seven tiles ahead, and the TMA load of the B box (1 stage: it is free again as
 //   soon as its MMA retires).
 //   Per four columns a thread runs
 //     - the (min,+) contraction over tokens: per token pair 2 broadcast 128-bit loads of L (token-major tile),
@@ -492,7 +492,7 @@ constexpr int kSwThreads = kSwWarps * 32;           // 512
 #ifdef IMP_SWEEP_TRACE
 __device__ unsigned long long g_sweep_trace[16 * 8];   // debug counters (profiles/r01_sweep_iterations.md)
 #endif
-constexpr int kTBufs = 4;                           // ring slots: TMEM accumulator of 64 columns + L/degree tile
+constexpr int kTBufs = 8;                           // ring slots: TMEM accumulator of 64 columns + L/degree tile (4 slots: 33.4 ms, 8: 32.9)
 constexpr int kLStages = kTBufs;
 
 template <int NQ1, int NQ2>
@@ -557,7 +557,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   // Producer work rotates over the 16 warps: warp n % 16 owns tile n and, from inside its own sweep, at non-blocking
   // probe points (five per tile), performs
-  //   step 1 (gates: tiles < n issued, B box n landed, ring slot n % 4 released by all 16 warps):
+  //   step 1 (gates: tiles < n issued, B box n landed, ring slot n % 8 released by all 16 warps):
   //           bulk copies of the L / degree tile n, the 16 tcgen05 MMAs of tile n, commits to bempty and full;
   //   step 2 (gate: the MMAs of tile n have retired = bempty): TMA load of B box n + 1 (single stage).
   // Every step runs on a whole, converged warp and the asynchronous instructions on the lane elect.sync picks:
