@@ -29,6 +29,13 @@ sys.path.insert(0, ROOT)
 N_PATCH, D_IN, N_PROTO, N_PATHWAYS = 16384, 512, 32, 6
 GROUP_SIZES = [82, 330, 513, 440, 1538, 451]
 WORKLOAD = "configs[1]: survival training, synthetic TCGA-shaped bags 16384x512, 32 prototypes, 6 pathways, bf16"
+
+
+def workload_label(patches, protos):
+    """The BASELINE configs[1] label; a run at other sizes (parity / smoke sizes) says so."""
+    if patches == N_PATCH and protos == N_PROTO:
+        return WORKLOAD
+    return "configs[1] shape at a reduced size (%dx512 patches, %d prototypes, 6 pathways, bf16): not the headline configuration" % (patches, protos)
 # dram__bytes_read.sum + dram__bytes_write.sum of one modularity_sweep launch from `ncu --set full`
 # (profiles/r01_ncu_full_final.md), keyed by bags per launch; None when not captured for that size
 SWEEP_TRAFFIC_PER_LAUNCH = {32: 423.1e6 + 62.2e6}
@@ -111,7 +118,7 @@ def run_reference(args):
         "impl": "reference", "metric": "wsi_bags_per_s_fwd_bwd", "value": val, "unit": "bags/s",
         "n_gpus": args.gpus, "steps": k, "warmup": w, "ms_per_step": 1e3 * t / k, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "bags_per_step": 1, "patches": args.patches, "prototypes": args.protos,
+        "config": {"workload": workload_label(args.patches, args.protos), "bags_per_step": 1, "patches": args.patches, "prototypes": args.protos,
                    "modularity": True},
         "cpu_baseline": {"value": val, "unit": "bags/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "bags/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -437,7 +444,7 @@ def run_ours(args):
             "metric": "wsi_bags_per_s_fwd_bwd", "value": value, "unit": "bags/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "bags_per_step_per_gpu": B, "patches": N, "prototypes": P, "pathways": N_PATHWAYS,
+            "config": {"workload": workload_label(N, P), "bags_per_step_per_gpu": B, "patches": N, "prototypes": P, "pathways": N_PATHWAYS,
                        "modularity": True, "dropout": 0.25, "missing_omics_fraction": args.missing_omics,
                        "l2": "inputs larger than L2: %.0f MiB of bf16 features per step per GPU" % (B * N * D_IN * 2 / 2 ** 20),
                        "parallelism": "dp%d" % world},
