@@ -36,11 +36,20 @@ def workload_label(patches, protos):
     if patches == N_PATCH and protos == N_PROTO:
         return WORKLOAD
     return "configs[1] shape at a reduced size (%dx512 patches, %d prototypes, 6 pathways, bf16): not the headline configuration" % (patches, protos)
-# dram__bytes_read.sum + dram__bytes_write.sum of one modularity_sweep launch from `ncu --set full`
-# (profiles/r01_ncu_full_final.md), keyed by bags per launch; None when not captured for that size
-SWEEP_TRAFFIC_PER_LAUNCH = {32: 423.1e6 + 62.2e6}
-# the same sum over one step's launches of the streaming kernels (path_net fwd, 2x pool fwd + merge, 2x dq, dz, dW1)
-STREAM_TRAFFIC_PER_STEP = {32: 3.26e9}
+
+
+def ncu_traffic(bags):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, per kernel, from the tracked summary of the
+    `ncu --set full` capture (profiles/ncu_traffic.json, written by profiles/summarize.py from the .ncu-rep of the
+    same bench command).  The file names the capture it came from; it applies only to the bags-per-step it was
+    captured at -- otherwise (or if absent) the traffic fields are null."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return {}, None
+    if int(t.get("bags_per_step", -1)) != int(bags):
+        return {}, None
+    return t.get("bytes_per_launch", {}), t.get("source")
 
 
 def parse():
@@ -104,7 +113,9 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    k = max(1, min(args.steps, 4))           # bounded: ~20 s of host work per slide
+    # bounded sample: one 16384-patch slide costs ~20 s of host work, so at most 4 timed steps of 1 slide each
+    # (the GPU arm runs `--steps` steps of 32 slides); the metric (bags/s) is per slide and comparable
+    k = max(1, min(args.steps, 4))
     w = min(args.warmup, 1)
     for _ in range(w):
         cpu_port_step(args.patches, args.protos)
@@ -118,8 +129,9 @@ def run_reference(args):
         "impl": "reference", "metric": "wsi_bags_per_s_fwd_bwd", "value": val, "unit": "bags/s",
         "n_gpus": args.gpus, "steps": k, "warmup": w, "ms_per_step": 1e3 * t / k, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_label(args.patches, args.protos), "bags_per_step": 1, "patches": args.patches, "prototypes": args.protos,
-                   "modularity": True},
+        "config": {"workload": workload_label(args.patches, args.protos).replace("bf16", "bf16 on the GPU arm; this CPU arm computes in f32"),
+                   "bags_per_step": 1, "patches": args.patches, "prototypes": args.protos, "modularity": True,
+                   "steps_note": "at most 4 timed steps of 1 slide (~20 s each) so that the arm ends within minutes"},
         "cpu_baseline": {"value": val, "unit": "bags/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "bags/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -167,6 +179,228 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference arithmetic, eager PyTorch on the GPU (the honest speed-up denominator)
+# ------------------------------------------------------------------------------------------------
+def gpu_eager_baseline(dev):
+    """path_net -> 2 prototype blocks -> compute_modularity for both token groups, forward + backward, written with
+    the ATen ops the reference launches (oracle.prototype_pool / modularity_literal restate umeml_gan.py:410,425-434
+    and ops/utils.py:188-228 literally, N x N and P x N x N tensors included).  fp32, TF32 off, 1 slide per step.
+    configs[0] (4096, P = 16) always; configs[1] (16384, P = 32 + 7) if it fits in HBM -- the OOM is reported."""
+    import torch
+    from oracle import imp_oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util_hotpath import block_tensors, make_params
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    names = ["in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias", "norm1.weight", "norm1.bias"]
+    out = {"device": torch.cuda.get_device_name(dev), "dtype": "f32 (TF32 off)", "kind": "port of the reference op sequence (oracle/imp_oracle.py) in eager PyTorch on the GPU",
+           "unit": "bags/s"}
+    for label, n, p in (("configs[0] 4096x512 P=16", 4096, 16), ("configs[1] 16384x512 P=32+7", 16384, 32)):
+        try:
+            params = {k: v.to(dev).requires_grad_(True) for k, v in make_params(0).items()}
+            blocks = [dict(zip(names, block_tensors(params, b))) for b in range(2)]
+            g = torch.Generator(device=dev).manual_seed(0)
+            x = torch.randn(n, D_IN, device=dev, generator=g)
+            p_proto = (torch.rand(p, 256, device=dev, generator=g) * 2 - 1) / p
+            tok = torch.rand(N_PATHWAYS + 1, 256, device=dev, generator=g).requires_grad_(True)
+            cot = torch.randn(p, 256, device=dev, generator=g) * 1e-2
+
+            def step():
+                for t in list(params.values()) + [tok]:
+                    t.grad = None
+                c, h = O.prototype_pool(x, p_proto, params["path_net.0.weight"], params["path_net.0.bias"], blocks)
+                loss = (c * cot).sum() + O.modularity_literal(c, h) + O.modularity_literal(tok, h)
+                loss.backward()
+            step()
+            torch.cuda.synchronize(dev)
+            k = 3
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(k):
+                step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / k
+            out[label] = {"value": 1e3 / ms, "ms_per_bag": ms, "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1)}
+        except torch.cuda.OutOfMemoryError as exc:
+            out[label] = {"value": None, "oom": str(exc)[:160]}
+        finally:
+            params = blocks = x = tok = None
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats(dev)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-GPU correctness record (rank 0 recomputes everything alone and compares)
+# ------------------------------------------------------------------------------------------------
+def run_dp_check(dev, rank, world):
+    """(1) slide-parallel: every rank runs fwd+bwd on its own two small bags, gradients are all-reduced (mean);
+    rank 0 then runs ALL bags in one process and compares every parameter gradient.  (2) giant-bag mode on a
+    4096-patch bag: sharded pooling (LSE merge) + sharded modularity against the single-GPU result."""
+    import torch
+    import torch.distributed as dist
+    from imp_b200 import model as M, modularity as MOD, ops, parallel as PAR, step as S
+
+    def rel(a, b):
+        return float(((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item())
+
+    P = 16
+    torch.manual_seed(4321)                                             # identical parameters on every rank
+    net = M.IMPHotPath(n_proto=P, dropout=0.0, seed=0).to(dev)
+    runner = S.HotPathStep(net, with_modularity=True).to(dev).train()
+
+    def data(r):
+        g = torch.Generator().manual_seed(900 + r)
+        lens = [384 + 64 * (r % 3), 200 + 17 * r]
+        x = torch.cat([torch.randn(n, D_IN, generator=g) for n in lens]).bfloat16()
+        omic = torch.rand(2, sum(GROUP_SIZES), generator=g)
+        cp = torch.randn(2, P, 256, generator=g) * 1e-2
+        co = torch.randn(2, N_PATHWAYS + 1, 256, generator=g) * 1e-2
+        return lens, x, omic, cp, co
+
+    def grads_of(rs, scale):
+        lens, xs, om, cps, cos = [], [], [], [], []
+        for r in rs:
+            l, x, o, cp, co = data(r)
+            lens += l; xs.append(x); om.append(o); cps.append(cp); cos.append(co)
+        cu = torch.tensor([0] + torch.tensor(lens).cumsum(0).tolist(), dtype=torch.int32, device=dev)
+        batch = {"x_packed": torch.cat(xs).to(dev), "cu_seqlens": cu, "max_len": max(lens), "omic": torch.cat(om).to(dev)}
+        for p in runner.parameters():
+            p.grad = None
+        loss = runner(batch, torch.cat(cps).to(dev) * scale, torch.cat(cos).to(dev) * scale)
+        loss.backward()
+        return [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in runner.parameters()]
+
+    grads_of([rank], 1.0)
+    S.allreduce_gradients(runner, world)
+    reduced = [p.grad.clone() for p in runner.parameters()]
+    out = {}
+    if rank == 0:
+        # mean over ranks of [sum_b c.cot + mean_b modularity] == [sum over all bags of c.cot/W + mean over all bags]
+        single = grads_of(list(range(world)), 1.0 / world)
+        out["slide_parallel_grad_rel_err_max"] = max(rel(a, b) for a, b in zip(reduced, single))
+        out["slide_parallel_what"] = "all-reduced (mean) gradients of %d ranks x 2 bags vs one process running all %d bags" % (world, 2 * world)
+    # ---- giant-bag mode ----
+    n = 4096
+    g = torch.Generator().manual_seed(77)
+    xg = torch.randn(n, D_IN, generator=g).bfloat16().to(dev)
+    cot = (torch.randn(1, P, 256, generator=g) * 1e-2).to(dev)
+    blocks = [ops.block_params(b) for b in net.proto_g_blocks]
+    a, b = PAR.shard_bounds(n, world)[rank]
+
+    def giant(x, cu, max_len, group, row0):
+        for p in net.parameters():
+            p.grad = None
+        c, h = ops.proto_fusion(x, cu, max_len, net.p_proto, net.path_net[0].weight, net.path_net[0].bias, blocks,
+                                shard_group=group)
+        cl = c.detach().clone().requires_grad_(True)
+        if group is not None:
+            t = MOD.modularity_terms_sharded(h, row0, n, cl, group=group)[0, 0]
+        else:
+            t = MOD.modularity_terms(h, cu, n, cl)[0, 0]
+        t.backward()
+        (c * cot).sum().backward()
+        return c.detach(), t.detach(), cl.grad, net.path_net[0].weight.grad.clone()
+
+    cs, ts, dcs, dws = giant(xg[a:b].contiguous(), torch.tensor([0, b - a], dtype=torch.int32, device=dev), max(1, b - a),
+                             dist.group.WORLD, a)
+    if rank == 0:
+        c1, t1, dc1, dw1 = giant(xg, torch.tensor([0, n], dtype=torch.int32, device=dev), n, None, 0)
+        out["sharded_pool_token_rel_err"] = rel(cs, c1)
+        out["sharded_pool_dw1_rel_err"] = rel(dws, dw1)
+        out["sharded_modularity_loss_rel_err"] = abs(float(ts) - float(t1)) / abs(float(t1))
+        out["sharded_modularity_grad_rel_err"] = rel(dcs, dc1)
+        out["sharded_what"] = "one %d-patch bag split by rows over %d ranks (LSE-merged pooling, two-phase modularity) vs one GPU" % (n, world)
+    dist.barrier()
+    return out
+
+
+def giant_measure(dev, rank, world, P, steps, warmup, with_single):
+    """configs[3]: ONE 120 000-patch bag, fwd + bwd incl. the modularity term, rows sharded over `world` ranks;
+    with_single: rank 0 also runs the whole bag alone (the strong-scaling denominator) and the merged tokens are
+    compared.  Returns a dict on rank 0 (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    from imp_b200 import _lib, model as M, modularity as MOD, ops, parallel as PAR
+    n = 120000
+    torch.manual_seed(1234)                                   # identical parameters on every rank
+    net = M.IMPHotPath(n_proto=P, dropout=0.0 if with_single else 0.25, seed=0).to(dev).train()
+    bounds = PAR.shard_bounds(n, world)
+    a, b = bounds[rank]
+
+    def shard(r):
+        lo, hi = bounds[r]
+        return torch.randn(hi - lo, D_IN, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + r)).bfloat16()
+
+    x = shard(rank)
+    cot = torch.randn(1, P, 256, device=dev, generator=torch.Generator(device=dev).manual_seed(100)) * 1e-2
+    group = dist.group.WORLD if world > 1 else None
+    params = [p for p in net.parameters()]
+    blocks = [ops.block_params(blk) for blk in net.proto_g_blocks]
+
+    def make_step(xs, rows, grp, row0):
+        cu = torch.tensor([0, rows], dtype=torch.int32, device=dev)
+
+        def step():
+            for p in params:
+                p.grad = None
+            c, h = ops.proto_fusion(xs, cu, max(1, rows), net.p_proto, net.path_net[0].weight, net.path_net[0].bias, blocks,
+                                    p_drop=net.dropout, seed=net._seed() if net.dropout > 0 else 0, shard_group=grp)
+            loss = (c * cot).sum()
+            if grp is not None:
+                loss = loss + MOD.modularity_terms_sharded(h, row0, n, c, group=grp)[0, 0]
+            else:
+                loss = loss + MOD.modularity_terms(h, cu, rows, c)[0, 0]
+            loss.backward()
+            return c.detach()
+        return step
+
+    def time_it(step, sync_group):
+        for _ in range(max(1, warmup)):
+            c = step()
+        torch.cuda.synchronize()
+        if sync_group:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            c = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if sync_group:
+            tms = torch.tensor([ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms / steps, c, _lib.launch_count() - l0
+
+    ms_n, c_n, launches = time_it(make_step(x, b - a, group, a), world > 1)
+    agree = 0.0
+    if world > 1:
+        cs = [torch.empty_like(c_n) for _ in range(world)]
+        dist.all_gather(cs, c_n.contiguous())
+        agree = max(float((ci - cs[0]).abs().max().item()) for ci in cs)    # merged tokens are identical on every rank
+    rec = None
+    if rank == 0:
+        rec = {"workload": "configs[3]: 1 slide of 120000x512 patches, %d prototypes, rows sharded over %d GPU(s), fwd+bwd incl. modularity" % (P, world),
+               "ms_per_step_sharded": ms_n, "n_gpus": world, "max_abs_token_difference_between_ranks": agree,
+               "gpu_launches": int(launches), "rows_per_rank_mib": round((b - a) * D_IN * 2 / 2 ** 20, 1)}
+        if with_single and world > 1:
+            xall = torch.cat([x] + [shard(r) for r in range(1, world)])
+            ms_1, c_1, _ = time_it(make_step(xall, n, None, 0), False)
+            rec["ms_per_step_1gpu"] = ms_1
+            rec["strong_scaling_speedup"] = ms_1 / ms_n
+            rec["token_max_abs_diff_sharded_vs_1gpu"] = float((c_1 - c_n).abs().max().item())
+            rec["token_rel_err_sharded_vs_1gpu"] = float(((c_1 - c_n).norm() / c_1.norm()).item())
+    if world > 1:
+        dist.barrier()
+    return rec
 
 
 # ------------------------------------------------------------------------------------------------
@@ -302,6 +536,7 @@ def run_ours(args):
 
     pk = per_kernel(recs, args.steps)
     pk_s = per_kernel(recs_s, args.steps)
+    traffic_tab, traffic_src = ncu_traffic(B)
     rows = B * N
     alg = {   # algorithmic bytes / flops per launch
         "pathnet_fwd": ("hbm", rows * D_IN * 2.0), "pathnet_dw": ("hbm", rows * D_IN * 2.0),
@@ -348,41 +583,58 @@ def run_ours(args):
             "issue bound, 92 cycles the ALU-pipe bound (19.5 FMNMX3 at 3.7 cycles + 10 other ALU instructions at 2, "
             "measured pipe rates in profiles/r01_sweep_iterations.md)"}
         roofline["cuda_core_issue"]["frac_of_alu_pipe_bound"] = round(92.0 / roofline["cuda_core_issue"]["sm_cycles_per_32_pairs"], 4)
-        roofline["traffic"] = SWEEP_TRAFFIC_PER_LAUNCH.get(B)
+        roofline["traffic"] = traffic_tab.get("modularity_sweep")
+        roofline["traffic_source"] = traffic_src
     # fused streaming path (the metric's 'fused-kernel HBM GB/s'): x read once forward + once backward
     stream_names = ["pathnet_fwd", "pool_fwd", "pool_merge", "pool_bwd_dq", "pool_bwd_dz", "reduce_dq", "reduce_db", "pathnet_dw",
                     "sum_partials", "cast_bf16"]
     stream_ms = sum(pk_s[k]["ms_per_step"] for k in stream_names if k in pk_s)
+    stream_traffic = None
+    if traffic_tab and all(k in traffic_tab for k in stream_names if k in pk_s):
+        stream_traffic = sum(traffic_tab[k] * pk_s[k]["launches_per_step"] for k in stream_names if k in pk_s)
     alg_stream = 2.0 * rows * D_IN * 2.0
     roofline_stream = {"bound": "hbm", "achieved": round(alg_stream / (stream_ms * 1e-3) / 1e9, 2) if stream_ms else None,
-                       "peak": hbm_peak, "unit": "GB/s", "traffic": STREAM_TRAFFIC_PER_STEP.get(B),
+                       "peak": hbm_peak, "unit": "GB/s", "traffic": stream_traffic, "traffic_source": traffic_src,
                        "kernels": [k for k in stream_names if k in pk_s], "kernel_ms_per_step": round(stream_ms, 4),
                        "algorithmic_bytes_per_step": alg_stream}
     if roofline_stream["achieved"]:
         roofline_stream["frac"] = round(roofline_stream["achieved"] / hbm_peak, 4)
 
-    # ---- e2e: reference batch layout in pinned host memory -> H2D -> strip/pack -> step -> D2H loss ----
-    # Every step copies its own batch from pinned host memory and its loss is read back on the host, all inside
-    # the timed region.  The copies run on a second stream into a double buffer (batch k+1 uploads while step k
-    # computes) and the loss of step k is read after step k+1 has been queued, as a training loop would do.
-    e2e = None
-    if not args.no_e2e:
+    # ---- e2e: a batch in pinned host memory -> H2D -> (strip/pack) -> step -> D2H loss, every step ----
+    # Two host layouts: the native wire format (imp_b200.wire: valid rows only, bf16, cu_seqlens) and
+    # the reference batch dict (img (B,N,512) fp32 as data_manager.py:395-403 collates it) as the compatibility path.
+    # The copies run on a second stream into a double buffer (batch k+1 uploads while step k computes) and the loss
+    # of step k is read after step k+1 has been queued, as a training loop would do.
+    def run_e2e(layout):
         Be = args.e2e_bags
-        img_h = torch.empty(Be, N, D_IN, dtype=torch.float32).pin_memory()
-        img_h.normal_(generator=torch.Generator().manual_seed(7 + rank))
         omic_h = torch.rand(Be, sum(GROUP_SIZES)).pin_memory()
+        if layout == "packed_bf16":
+            from imp_b200 import wire
+            feats = torch.empty(Be * N, D_IN, dtype=torch.float32).normal_(generator=torch.Generator().manual_seed(7 + rank))
+            host = wire.pack_bags([feats[i * N:(i + 1) * N] for i in range(Be)], pin=True, strip=False)
+            del feats
+            src, cu_e = host["x_packed"], host["cu_seqlens"].to(dev)
+            mk = lambda: torch.empty(Be * N, D_IN, device=dev, dtype=torch.bfloat16)
+            as_batch = lambda sl: {"x_packed": sl["img"], "cu_seqlens": cu_e, "max_len": N, "omic": sl["omic"]}
+            desc = "imp_b200.wire packed batch: x (B*%d,512) bf16 pinned + cu_seqlens, omic (B,3354) fp32" % N
+        else:
+            src = torch.empty(Be, N, D_IN, dtype=torch.float32).pin_memory()
+            src.normal_(generator=torch.Generator().manual_seed(7 + rank))
+            mk = lambda: torch.empty(Be, N, D_IN, device=dev)
+            as_batch = lambda sl: {"img": sl["img"], "omic": sl["omic"]}
+            desc = "reference batch dict: img (B,%d,512) fp32 pinned, omic (B,3354) fp32" % N
         cp, co = cot_p[:Be].contiguous(), cot_o[:Be].contiguous()
         sink = torch.empty(2, dtype=torch.float32).pin_memory()
         copy_stream = torch.cuda.Stream(device=dev)
         main_stream = torch.cuda.current_stream(dev)
-        dbuf = [{"img": torch.empty(Be, N, D_IN, device=dev), "omic": torch.empty(Be, sum(GROUP_SIZES), device=dev),
+        dbuf = [{"img": mk(), "omic": torch.empty(Be, sum(GROUP_SIZES), device=dev),
                  "ready": torch.cuda.Event(), "free": torch.cuda.Event()} for _ in range(2)]
         state = {"k": 0, "pending": None}
 
         def upload(slot):
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(slot["free"])             # the step that last read this buffer has finished
-                slot["img"].copy_(img_h, non_blocking=True)
+                slot["img"].copy_(src, non_blocking=True)
                 slot["omic"].copy_(omic_h, non_blocking=True)
                 slot["ready"].record(copy_stream)
 
@@ -399,7 +651,7 @@ def run_ours(args):
                     main_stream.wait_event(dbuf[0]["ready"])
                     sl["img"].copy_(dbuf[0]["img"]) if i else None
                     sl["omic"].copy_(dbuf[0]["omic"]) if i else None
-                    graphs[i] = S.GraphedStep(runner).capture({"img": sl["img"], "omic": sl["omic"]}, cp, co, lengths=None)
+                    graphs[i] = S.GraphedStep(runner).capture(as_batch(sl), cp, co, lengths=None)
             except Exception:
                 graphs = [None, None]
 
@@ -413,22 +665,44 @@ def run_ours(args):
                 if world > 1:
                     S.allreduce_gradients(runner, world)
             else:
-                loss = one_step({"img": cur["img"], "omic": cur["omic"]}, cp, co, True, lengths=None)
+                loss = one_step(as_batch(cur), cp, co, True, lengths=None)
             cur["free"].record(main_stream)
             if state["pending"] is not None:                      # D2H of the previous step's loss
-                ev, slot_i = state["pending"]
-                ev.synchronize()
+                state["pending"].synchronize()
             sink[k % 2:k % 2 + 1].copy_(loss.detach().reshape(1), non_blocking=True)
             ev = torch.cuda.Event(); ev.record(main_stream)
-            state["pending"] = (ev, k % 2)
+            state["pending"] = ev
             state["k"] = k + 1
 
         n_e = max(2, args.steps // 2)
         ms_e, _, _, _ = timed(e2e_step, n_e, min(args.warmup, 2))
-        e2e = {"value": world * Be * n_e / (ms_e * 1e-3), "unit": "bags/s",
-               "h2d_bytes_per_step": int(img_h.numel() * 4 + omic_h.numel() * 4), "d2h_bytes_per_step": 4,
-               "bags_per_step": Be, "host_layout": "reference batch dict: img (B,%d,512) fp32 pinned, omic (B,3354) fp32" % N,
-               "overlap": "H2D double-buffered on a copy stream; loss read back one step behind; step replayed from a CUDA graph per buffer slot" if graphs[0] is not None else "H2D double-buffered on a copy stream; loss read back one step behind; eager launches"}
+        for g_ in graphs:
+            if g_ is not None:
+                g_.close()
+        return {"value": world * Be * n_e / (ms_e * 1e-3), "unit": "bags/s",
+                "h2d_bytes_per_step": int(src.numel() * src.element_size() + omic_h.numel() * 4), "d2h_bytes_per_step": 4,
+                "bags_per_step": Be, "host_layout": desc,
+                "overlap": ("H2D double-buffered on a copy stream; loss read back one step behind; "
+                            + ("step replayed from a CUDA graph per buffer slot" if graphs[0] is not None else "eager launches"))}
+
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e("packed_bf16")
+        torch.cuda.empty_cache()
+        e2e["reference_layout"] = run_e2e("reference_fp32")
+        torch.cuda.empty_cache()
+
+    # ---- the reference arithmetic in eager PyTorch ON THIS GPU (BASELINE.md 5 / SURVEY 8(d)): same ATen op sequence
+    #      as umeml_gan.py:410,425-434 + ops/utils.py:188-228 (materialises N x N and P x N x N), fp32, TF32 off ----
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        gpu_eager = gpu_eager_baseline(dev)
+
+    # ---- multi-GPU correctness + the giant-bag strong-scaling record, so that the scaling run carries them ----
+    dp_check = giant = None
+    if world > 1:
+        dp_check = run_dp_check(dev, rank, world)
+        giant = giant_measure(dev, rank, world, P, steps=3, warmup=2, with_single=True)
 
     # ---- CPU baseline (oracle port), rank 0, N = 1 only ----
     cpu = None
@@ -452,7 +726,8 @@ def run_ours(args):
                                "what": "same step without the O(N^2) modularity term"},
             "launch_mode": graph_note, "eager": eager,
             "roofline": roofline, "roofline_streaming": roofline_stream, "kernels": kernels_out,
-            "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": e2e, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "dp_check": dp_check, "giant": giant,
+            "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(out))
     if world > 1:
@@ -511,7 +786,6 @@ def run_giant(args):
     A step = forward + backward of that one bag (strong scaling: the bag is fixed, the ranks split it)."""
     import torch
     import torch.distributed as dist
-    from imp_b200 import _lib, model as M, modularity as MOD, ops, parallel as PAR
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -519,62 +793,18 @@ def run_giant(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n, P = 120000, args.protos
-    torch.manual_seed(1234)                                   # identical parameters on every rank
-    net = M.IMPHotPath(n_proto=P, dropout=0.25, seed=0).to(dev).train()
-    a, b = PAR.shard_bounds(n, world)[rank]
-    gen = torch.Generator(device=dev).manual_seed(100)
-    x = torch.randn(b - a, D_IN, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + rank)).bfloat16()
-    cot = torch.randn(1, P, 256, device=dev, generator=gen) * 1e-2
-    cu = torch.tensor([0, b - a], dtype=torch.int32, device=dev)
-    group = dist.group.WORLD if world > 1 else None
-    params = [p for p in net.parameters()]
-    blocks = [ops.block_params(blk) for blk in net.proto_g_blocks]
-
-    def step():
-        for p in params:
-            p.grad = None
-        c, h = ops.proto_fusion(x, cu, max(1, b - a), net.p_proto, net.path_net[0].weight, net.path_net[0].bias, blocks,
-                                p_drop=0.25, seed=net._seed(), shard_group=group)
-        loss = (c * cot).sum()
-        if world > 1:
-            loss = loss + MOD.modularity_terms_sharded(h, a, n, c, group=group)[0, 0]
-        else:
-            loss = loss + MOD.modularity_terms(h, cu, n, c)[0, 0]
-        loss.backward()
-        return c
-
-    for _ in range(max(1, args.warmup)):
-        c = step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = _lib.launch_count()
-    e0.record()
-    for _ in range(args.steps):
-        c = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - l0
-    agree = 0.0
-    if world > 1:
-        tms = torch.tensor([ms], device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-        cs = [torch.empty_like(c) for _ in range(world)]
-        dist.all_gather(cs, c.contiguous())
-        agree = max(float((ci - cs[0]).abs().max().item()) for ci in cs)    # merged tokens are identical on every rank
+    rec = giant_measure(dev, rank, world, args.protos, args.steps, max(1, args.warmup), with_single=False)
     if rank == 0:
+        ms = rec["ms_per_step_sharded"]
         print(json.dumps({
-            "metric": "giant_bags_per_s_fwd_bwd", "value": args.steps / (ms * 1e-3), "unit": "bags/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "metric": "giant_bags_per_s_fwd_bwd", "value": 1e3 / ms, "unit": "bags/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs[3]: giant-bag stress, 1 slide of 120000x512 patches, %d prototypes, rows sharded over %d GPU(s)" % (P, world),
-                       "modularity": True, "dropout": 0.25, "l2": "inputs larger than L2: %.0f MiB of bf16 features per rank" % ((b - a) * D_IN * 2 / 2 ** 20),
+            "config": {"workload": rec["workload"], "modularity": True, "dropout": 0.25,
+                       "l2": "inputs larger than L2: %.0f MiB of bf16 features per rank" % rec["rows_per_rank_mib"],
                        "parallelism": "rows%d" % world},
-            "max_abs_token_difference_between_ranks": agree, "gpu_launches": int(launches),
+            "max_abs_token_difference_between_ranks": rec["max_abs_token_difference_between_ranks"],
+            "gpu_launches": rec["gpu_launches"],
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -24,15 +24,29 @@ def header_symbols(header: str = HEADER):
     return sorted(set(re.findall(r"\b(imp_[a-z0-9_]+)\s*\(", text)))
 
 
+def header_abi_version(header: str = HEADER) -> int:
+    m = re.search(r"#define\s+IMP_ABI_VERSION\s+(\d+)", open(header).read())
+    if not m:
+        raise ImpError("IMP_ABI_VERSION not found in %s" % header)
+    return int(m.group(1))
+
+
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            from . import build as _build
+        from . import build as _build
+        try:                                   # digest-based and incremental: a stale library is rebuilt, a fresh one is kept
             _build.build()
+        except RuntimeError:
+            if not os.path.exists(LIB_PATH):   # no nvcc and no prebuilt library: there is nothing to fall back to
+                raise
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.imp_last_error.restype = ctypes.c_char_p
         _lib.imp_abi_version.restype = ctypes.c_int
+        want = header_abi_version()
+        got = int(_lib.imp_abi_version())
+        if got != want:
+            raise ImpError("libimp_sm100.so reports ABI %d, include/imp_hotpath.h declares %d: rebuild the library" % (got, want))
         for name in header_symbols():
             fn = getattr(_lib, name)          # AttributeError if the .so lacks a declared symbol
             if name.endswith("_bytes"):

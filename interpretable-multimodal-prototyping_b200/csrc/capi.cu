@@ -4,6 +4,10 @@
 #include "common.cuh"
 #include "launchers.h"
 #include "../../include/imp_hotpath.h"
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 
 thread_local char g_imp_err[512] = {0};
 
@@ -47,14 +51,33 @@ int imp_make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt,
   return IMP_OK;
 }
 
+// SM count of the CURRENT device (a process may drive several GPUs: cached per device ordinal)
 int imp_num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (!n) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: remember what was granted per
+// (kernel, device) so that a second GPU driven by the same process gets its own opt-in.
+int imp_ensure_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> granted;
+  int dev = 0;
+  IMP_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& g = granted[std::make_pair(kernel, dev)];
+  if (bytes > g) {
+    IMP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    g = bytes;
+  }
+  return IMP_OK;
 }
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
@@ -118,10 +141,18 @@ extern "C" int imp_profile_collect(const char** names, float* ms, int max_record
   return n;
 }
 
-static std::atomic<const uint32_t*> g_seed_offset{nullptr};
-const uint32_t* imp_seed_offset_ptr() { return g_seed_offset.load(); }
+// one seed-offset word per device ordinal (the pointer is device memory of the current device)
+static std::atomic<const uint32_t*> g_seed_offset[64];
+const uint32_t* imp_seed_offset_ptr() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  return g_seed_offset[dev].load();
+}
 extern "C" int imp_set_seed_offset(const unsigned* device_word) {
-  g_seed_offset.store(device_word);
+  int dev = 0;
+  IMP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) IMP_FAIL(IMP_ERR_ARG, "imp_set_seed_offset: device ordinal %d out of range", dev);
+  g_seed_offset[dev].store(device_word);
   return IMP_OK;
 }
 

@@ -48,6 +48,7 @@ int imp_make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt,
                      uint64_t inner, uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner,
                      uint32_t box_outer, CUtensorMapSwizzle swz);
 int imp_num_sms();
+int imp_ensure_smem(const void* kernel, size_t bytes);   // per-(kernel, device) dynamic shared-memory opt-in
 // device word XOR-ed into every dropout seed (imp_set_seed_offset); null = none.  Lets a captured CUDA graph
 // draw a fresh keep-mask on every replay: the graph itself advances the word.
 const uint32_t* imp_seed_offset_ptr();

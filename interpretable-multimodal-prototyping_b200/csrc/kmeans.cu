@@ -4,11 +4,13 @@
 //
 //   assign[n] = argmin_k ( ||x_n||^2 + ||mu_k||^2 - 2 x_n . mu_k )      x (N,D) fp32, mu (K,D) fp32, K <= 64
 //
-// fp32 FMA on CUDA cores (exact agreement with the fp32 oracle is required, so no reduced-precision
-// tensor-core path).  Algorithmically HBM-bound (N*D*4 bytes read once), but 2*K FLOP per byte put the fp32 pipe
-// right at the roofline: the scalar FFMA rate (64 lanes/clk/SM) is too slow, so the inner product runs on packed
-// FFMA2 (two centroids per instruction, x broadcast) with RPT rows per thread sharing every broadcast load of
-// mu^T from shared memory.  One TMA producer warp streams [256*RPT rows][16 floats] tiles (64-byte swizzle);
+// Two paths, both fp32-accurate (exact agreement with the fp32 oracle is required, so nothing is computed in
+// reduced precision):  (1) K <= 32: tcgen05 tensor cores on three-way bf16 splits of x and mu (every fp32 number is
+// exactly hi + mid + lo in bf16; the nine partial products are accumulated in fp32 in TMEM), kmeans_assign_tc_kernel
+// below -- the default for configs[4];  (2) K > 32 or large D: fp32 FMA on CUDA cores.  Algorithmically HBM-bound
+// (N*D*4 bytes read once), but 2*K FLOP per byte put the fp32 pipe right at the roofline: the scalar FFMA rate
+// (64 lanes/clk/SM) is too slow, so the inner product runs on packed FFMA2 (two centroids per instruction, x
+// broadcast) with RPT rows per thread sharing every broadcast load of mu^T from shared memory.  One TMA producer warp streams [256*RPT rows][16 floats] tiles (64-byte swizzle);
 // 8 consumer warps, thread = RPT rows.  The accumulation order over the features is the oracle's
 // (ascending d, one fma per (row, centroid, d)), so distances are bit-identical to the scalar kernel.
 // Also: the Lloyd update (sums and counts per centroid).
@@ -435,11 +437,7 @@ template <int KP, int RPT>
 int run_assign(const CUtensorMap& tm, KmParams p, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)kStages * 256 * RPT * kKC * 4 + (size_t)p.D * KP * 4 + KP * 4 + 2 * kStages * 8 + 64;
   if (smem > 227 * 1024) IMP_FAIL(IMP_ERR_ARG, "kmeans_assign: D=%d with %d centroids exceeds shared memory", p.D, p.K);
-  static size_t attr = 0;
-  if (smem > attr) {
-    IMP_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<KP, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  { const int rc_ = imp_ensure_smem((const void*)kmeans_assign_kernel<KP, RPT>, smem); if (rc_) return rc_; }
   p.num_tiles = (p.N + 256 * RPT - 1) / (256 * RPT);
   const int grid = std::min(p.num_tiles, imp_num_sms());
   IMP_LAUNCH("kmeans_assign", st, kmeans_assign_kernel<KP, RPT><<<grid, kThreads, smem, st>>>(tm, p));
@@ -467,12 +465,10 @@ int launch_kmeans_assign(const float* x, const float* mu, int N, int D, int K, i
     const size_t smem = 1024 + 2 * kTcXStage + 3 * kTcPart + (size_t)3 * KPt * D * 2 + (KPt + kTcRows) * 4 + 256;
     const int grid = std::min(q.num_tiles, imp_num_sms());
     if (KPt == 16) {
-      static size_t attr = 0;
-      if (smem > attr) { IMP_CUDA(cudaFuncSetAttribute(kmeans_assign_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+      { const int rc_ = imp_ensure_smem((const void*)kmeans_assign_tc_kernel<16>, smem); if (rc_) return rc_; }
       IMP_LAUNCH("kmeans_assign", st, kmeans_assign_tc_kernel<16><<<grid, kTcThreads, smem, st>>>(tm, q));
     } else {
-      static size_t attr = 0;
-      if (smem > attr) { IMP_CUDA(cudaFuncSetAttribute(kmeans_assign_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+      { const int rc_ = imp_ensure_smem((const void*)kmeans_assign_tc_kernel<32>, smem); if (rc_) return rc_; }
       IMP_LAUNCH("kmeans_assign", st, kmeans_assign_tc_kernel<32><<<grid, kTcThreads, smem, st>>>(tm, q));
     }
     return IMP_OK;
@@ -497,11 +493,7 @@ int launch_kmeans_update(const float* x, const int* assign, int N, int D, int K,
   if (D % 4 != 0) IMP_FAIL(IMP_ERR_ARG, "kmeans_update: D=%d must be a multiple of 4", D);
   const size_t smem = (size_t)K * D * 4 + (size_t)K * 4;
   if (smem > 200 * 1024) IMP_FAIL(IMP_ERR_ARG, "kmeans_update: K*D too large for shared accumulators");
-  static size_t attr = 0;
-  if (smem > attr) {
-    IMP_CUDA(cudaFuncSetAttribute(kmeans_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  { const int rc_ = imp_ensure_smem((const void*)kmeans_update_kernel, smem); if (rc_) return rc_; }
   const int grid = std::min((N + 63) / 64, 2 * imp_num_sms());
   IMP_LAUNCH("kmeans_update", st, kmeans_update_kernel<<<grid, 256, smem, st>>>(x, assign, sums, counts, N, D, K));
   return IMP_OK;

@@ -1031,11 +1031,7 @@ int quads1(int P1) { return P1 <= 8 ? 2 : (P1 <= 16 ? 4 : 8); }
 int quads2(int P2) { return P2 == 0 ? 0 : 2; }
 
 int run_degrees(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p, dim3 grid, cudaStream_t st) {
-  static bool done = false;
-  if (!done) {
-    IMP_CUDA(cudaFuncSetAttribute(modularity_degrees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDegSmem));
-    done = true;
-  }
+  { const int rc_ = imp_ensure_smem((const void*)modularity_degrees_kernel, kDegSmem); if (rc_) return rc_; }
   IMP_LAUNCH("modularity_degrees_gram", st, modularity_degrees_kernel<<<grid, kThreads, kDegSmem, st>>>(ta, tb, p));
   return IMP_OK;
 }
@@ -1044,11 +1040,7 @@ template <int NQ1, int NQ2, bool LASTPAD = false>
 int run_sweep(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p, dim3 grid, cudaStream_t st) {
   constexpr size_t smem = sweep_smem<NQ1, NQ2>();
   static_assert(smem <= 227 * 1024, "modularity_sweep shared memory");
-  static bool done = false;
-  if (!done) {
-    IMP_CUDA(cudaFuncSetAttribute(modularity_sweep_kernel<NQ1, NQ2, LASTPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    done = true;
-  }
+  { const int rc_ = imp_ensure_smem((const void*)modularity_sweep_kernel<NQ1, NQ2, LASTPAD>, smem); if (rc_) return rc_; }
   IMP_LAUNCH("modularity_sweep", st, modularity_sweep_kernel<NQ1, NQ2, LASTPAD><<<grid, kSwThreads, smem, st>>>(ta, tb, p));
   return IMP_OK;
 }
@@ -1056,11 +1048,7 @@ int run_sweep(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p,
 template <int PTPAD>
 int run_prep(const PrepParams& pp, cudaStream_t st) {
   constexpr size_t smem = prep_smem<PTPAD>();
-  static bool done = false;
-  if (!done) {
-    IMP_CUDA(cudaFuncSetAttribute(modularity_prep_kernel<PTPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    done = true;
-  }
+  { const int rc_ = imp_ensure_smem((const void*)modularity_prep_kernel<PTPAD>, smem); if (rc_) return rc_; }
   IMP_LAUNCH("modularity_prep", st, modularity_prep_kernel<PTPAD><<<(pp.row_hi - pp.row_lo + 63) / 64, 256, smem, st>>>(pp));
   return IMP_OK;
 }
@@ -1233,11 +1221,7 @@ int launch_modularity_execute(const bf16* h_local, int local_rows, int row_lo, i
 #define IMP_FIN(PT)                                                                                                    \
   do {                                                                                                                  \
     constexpr size_t smem = finish_tc_smem<PT>();                                                                       \
-    static bool done = false;                                                                                           \
-    if (!done) {                                                                                                        \
-      IMP_CUDA(cudaFuncSetAttribute(modularity_finish_tc_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      done = true;                                                                                                      \
-    }                                                                                                                   \
+  { const int rc_ = imp_ensure_smem((const void*)modularity_finish_tc_kernel<PT>, smem); if (rc_) return rc_; }                                                                                                                   \
     IMP_LAUNCH("modularity_finish", st, modularity_finish_tc_kernel<PT><<<fgrid, kFtThreads, smem, st>>>(th, fp));     \
   } while (0)
   switch (PtPad) {

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) omic_fwd_kernel(const OmicParams p) {
     if (p.drop_thresh) {
       const uint32_t seed = p.seed ^ (p.seed_offset ? __ldg(p.seed_offset) : 0u);
       const uint32_t hsh = mix32(seed ^ (((uint32_t)(b * p.K + k) * 256u + (uint32_t)f) * 0x9E3779B1u));
-      v = ((hsh & 0xffu) >= p.drop_thresh) ? v * p.keep_scale : 0.f;
+      v = ((hsh & 0xffffu) >= p.drop_thresh) ? v * p.keep_scale : 0.f;
     }
     p.out[((size_t)b * p.K + k) * kD + f] = v;
   }
@@ -174,8 +174,8 @@ static int fill_params(OmicParams& p, const float* x, const int* mask, const flo
   for (int k = 0; k <= K; ++k) p.goff[k] = group_offsets[k];
   for (int k = 0; k < K; ++k)
     if (p.goff[k + 1] <= p.goff[k]) IMP_FAIL(IMP_ERR_ARG, "omic: group %d is empty", k);
-  p.drop_thresh = (uint32_t)(p_drop * 256.f + 0.5f);
-  p.keep_scale = p.drop_thresh ? 256.f / (256.f - (float)p.drop_thresh) : 1.f;
+  p.drop_thresh = (uint32_t)(p_drop * 65536.f + 0.5f);
+  p.keep_scale = p.drop_thresh ? 65536.f / (65536.f - (float)p.drop_thresh) : 1.f;
   return IMP_OK;
 }
 
@@ -190,11 +190,7 @@ int launch_omic_fwd(const float* x, const int* mask, const float* means, const i
   p.out = out;
   const size_t smem = (size_t)kBB * gmax * sizeof(float);
   if (smem > 200 * 1024) IMP_FAIL(IMP_ERR_ARG, "omic: gene group of %d genes exceeds the staging buffer", gmax);
-  static size_t attr = 0;
-  if (smem > attr) {
-    IMP_CUDA(cudaFuncSetAttribute(omic_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  { const int rc_ = imp_ensure_smem((const void*)omic_fwd_kernel, smem); if (rc_) return rc_; }
   IMP_LAUNCH("omic_fwd", st, omic_fwd_kernel<<<dim3(kD / 8, K, (B + kBB - 1) / kBB), 256, smem, st>>>(p));
   return IMP_OK;
 }

@@ -28,7 +28,7 @@ struct FwdParams {
   int num_tiles;
   int kdim;               // 512 (multiple of 64)
   float keep_scale;       // 1/(1-p)
-  uint32_t drop_thresh;   // keep element iff (hash byte) >= drop_thresh ; 0 => no dropout
+  uint32_t drop_thresh;   // keep element iff (16 hash bits) >= drop_thresh = round(65536 p); 0 => no dropout
   uint32_t seed;
   const uint32_t* seed_offset;   // device word XOR-ed into the seed, or null
 };
@@ -132,10 +132,13 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #pragma unroll
           for (int e = 0; e < 4; ++e) f[e] = fmaxf(__uint_as_float(v[j + e]) + s_bias[col0 + j + e], 0.f);
           if (p.drop_thresh) {
-            uint32_t hsh = mix32(seed ^ ((uint32_t)row * 64u + (uint32_t)((col0 + j) >> 2)) * 0x9E3779B1u);
+            // 16 hash bits per element (p is quantised to 1/65536): two mixed words per group of four columns
+            const uint32_t h0 = mix32(seed ^ ((uint32_t)row * 64u + (uint32_t)((col0 + j) >> 2)) * 0x9E3779B1u);
+            const uint32_t h1 = mix32(h0 + 0x6a09e667u);
+            const uint32_t bits[4] = {h0 & 0xffffu, h0 >> 16, h1 & 0xffffu, h1 >> 16};
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              f[e] = (((hsh >> (8 * e)) & 0xffu) >= p.drop_thresh) ? f[e] * p.keep_scale : 0.f;
+              f[e] = (bits[e] >= p.drop_thresh) ? f[e] * p.keep_scale : 0.f;
           }
           packed[j / 2] = pack_bf16x2(f[0], f[1]);
           packed[j / 2 + 1] = pack_bf16x2(f[2], f[3]);
@@ -317,15 +320,11 @@ int launch_pathnet_fwd(const bf16* x, const bf16* w1, const float* b1, bf16* h, 
   FwdParams p;
   p.bias = b1; p.h = h; p.rows = rows; p.kdim = kdim;
   p.num_tiles = (rows + kBM - 1) / kBM;
-  p.drop_thresh = (uint32_t)(p_drop * 256.f + 0.5f);
-  p.keep_scale = p.drop_thresh ? 256.f / (256.f - (float)p.drop_thresh) : 1.f;
+  p.drop_thresh = (uint32_t)(p_drop * 65536.f + 0.5f);
+  p.keep_scale = p.drop_thresh ? 65536.f / (65536.f - (float)p.drop_thresh) : 1.f;
   p.seed = seed;
   p.seed_offset = imp_seed_offset_ptr();
-  static bool attr_done = false;
-  if (!attr_done) {
-    IMP_CUDA(cudaFuncSetAttribute(pathnet_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
-    attr_done = true;
-  }
+  { const int rc_ = imp_ensure_smem((const void*)pathnet_fwd_kernel, kFwdSmem); if (rc_) return rc_; }
   int grid = min(p.num_tiles, imp_num_sms());
   IMP_LAUNCH("pathnet_fwd", st, pathnet_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(tm_x, tm_w, p));
   return IMP_OK;
@@ -364,11 +363,7 @@ int launch_pathnet_dw(const bf16* dz, const bf16* x, float* dw, float* workspace
   p.kblocks_total = (rows + kDwBK - 1) / kDwBK;
   p.ksplit = max(1, min(imp_num_sms() / ntile, p.kblocks_total));
   p.lbo = kDwBK * 128; p.sbo = 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    IMP_CUDA(cudaFuncSetAttribute(pathnet_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem));
-    attr_done = true;
-  }
+  { const int rc_ = imp_ensure_smem((const void*)pathnet_dw_kernel, kDwSmem); if (rc_) return rc_; }
   IMP_LAUNCH("pathnet_dw", st, pathnet_dw_kernel<<<p.ksplit * ntile, kDwThreads, kDwSmem, st>>>(tm_dz, tm_x, p));
   return launch_sum_partials(workspace, dw, p.ksplit, (size_t)kD * kin, 1.f, accumulate, st);
 }

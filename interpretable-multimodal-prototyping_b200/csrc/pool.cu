@@ -736,11 +736,7 @@ void split_plan(int max_len, int B, int P, int* nsplit, int* tiles_per_split) {
 template <int PP, int STAGES>
 int run_fwd(const CUtensorMap& tm, const PoolFwdParams& p, int B, cudaStream_t st) {
   constexpr size_t smem = fwd_smem<PP, STAGES>();
-  static bool done = false;
-  if (!done) {
-    IMP_CUDA(cudaFuncSetAttribute(pool_fwd_kernel<PP, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    done = true;
-  }
+  { const int rc_ = imp_ensure_smem((const void*)pool_fwd_kernel<PP, STAGES>, smem); if (rc_) return rc_; }
   IMP_LAUNCH("pool_fwd", st, pool_fwd_kernel<PP, STAGES><<<dim3(p.nsplit, B), kThreads, smem, st>>>(tm, p));
   return IMP_OK;
 }
@@ -748,11 +744,7 @@ template <int PP, int NB, int STAGES>
 int run_bwd(const CUtensorMap& tm, const PoolBwdParams& p, int B, cudaStream_t st) {
   constexpr size_t smem = bwd_smem<PP, NB, STAGES>();
   static_assert(smem <= 227 * 1024, "pool_bwd shared memory");
-  static bool done = false;
-  if (!done) {
-    IMP_CUDA(cudaFuncSetAttribute(pool_bwd_kernel<PP, NB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    done = true;
-  }
+  { const int rc_ = imp_ensure_smem((const void*)pool_bwd_kernel<PP, NB, STAGES>, smem); if (rc_) return rc_; }
   IMP_LAUNCH("pool_bwd_dq", st, pool_bwd_kernel<PP, NB, STAGES><<<dim3(p.nsplit, B), kThreads, smem, st>>>(tm, p));
   return IMP_OK;
 }
@@ -761,11 +753,7 @@ template <int PP, int NB>
 int run_dz(const CUtensorMap& tm, const DzParams& p, int B, cudaStream_t st) {
   constexpr size_t smem = dz_smem<PP, NB>();
   static_assert(smem <= 227 * 1024, "pool_bwd_dz shared memory");
-  static bool done = false;
-  if (!done) {
-    IMP_CUDA(cudaFuncSetAttribute(pool_bwd_dz_kernel<PP, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    done = true;
-  }
+  { const int rc_ = imp_ensure_smem((const void*)pool_bwd_dz_kernel<PP, NB>, smem); if (rc_) return rc_; }
   IMP_LAUNCH("pool_bwd_dz", st, pool_bwd_dz_kernel<PP, NB><<<dim3(p.nsplit, B), kZThreads, smem, st>>>(tm, p));
   return IMP_OK;
 }

@@ -166,40 +166,71 @@ def modularity(h: torch.Tensor, cu_seqlens: torch.Tensor, max_len: int, chat: to
     return loss, dchat
 
 
+_shard_cache = {}
+
+
+def _cached(name: str, nbytes: int, device) -> torch.Tensor:
+    """Reusable byte buffer for the sharded path (the 80 MB modularity workspace, the exchange staging)."""
+    key = (name, device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _shard_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _shard_cache[key] = buf
+    return buf
+
+
+def _exchange_sections(ws: torch.Tensor, base: int, unit: int, windows, per_units: int, rank: int, name: str, group):
+    """Every rank owns the byte range [base + lo*unit, base + hi*unit) of ``ws`` (its window ``(lo, hi)`` of
+    ``windows``, in units); after the call every rank holds all of them.  One ``all_gather_into_tensor`` of equal
+    ``per_units * unit`` chunks through a staging buffer (the last windows may be shorter or empty, so the padded
+    chunks cannot be gathered in place), then one device copy per remote window."""
+    import torch.distributed as dist
+    world = len(windows)
+    chunk = per_units * unit
+    if chunk == 0:
+        return
+    stage = _cached(name, (world + 1) * chunk, ws.device)
+    send, recv = stage[:chunk], stage[chunk:(world + 1) * chunk]
+    lo, hi = windows[rank]
+    if hi > lo:
+        send[:(hi - lo) * unit].copy_(ws[base + lo * unit: base + hi * unit])
+    dist.all_gather_into_tensor(recv, send, group=group)
+    for r, (a, b) in enumerate(windows):
+        if r != rank and b > a:
+            ws[base + a * unit: base + b * unit].copy_(recv[r * chunk: r * chunk + (b - a) * unit])
+
+
 def modularity_sharded(h_local: torch.Tensor, row_offset: int, total_rows: int, chat: torch.Tensor, n_tok1: int,
                        n_tok2: int, temp: float, group) -> Tuple[torch.Tensor, torch.Tensor]:
-    """One bag of ``total_rows`` patches whose rows [row_offset, row_offset + h_local.shape[0]) live on this rank
-    (row_offset a multiple of 64; ranks in rank order cover [0,total_rows) without gaps).  Returns the GLOBAL
-    (loss (1,2), dchat (1,Pt,256)), identical on every rank of ``group``: prepare -> exchange of xh / fixed-point
-    assignments / column sums / sign flag -> sweep of the local rows -> sum of the partial results."""
+    """One bag of ``total_rows`` patches sharded by ``parallel.shard_bounds(total_rows, world)``: this rank holds the
+    rows [row_offset, row_offset + h_local.shape[0]).  Returns the GLOBAL (loss (1,2), dchat (1,Pt,256)), identical on
+    every rank of ``group``: prepare (local rows) -> exchange of x_hat / fixed-point assignments (one all-gather
+    each; the windows are known on the host, no device->host sync) and column sums / sign flag (all-reduce) ->
+    sweep of the local rows against all columns -> sum of the partial results."""
     import torch.distributed as dist
+    from . import parallel
     _chk(h_local, torch.bfloat16, "h_local"); _chk(chat, torch.float32, "chat")
     dev = chat.device
     local_rows = int(h_local.shape[0])
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    windows = parallel.shard_bounds(int(total_rows), world, 64)
+    # validated BEFORE the first collective: a rank that raised inside them would leave the others hanging
+    if (int(row_offset), int(row_offset) + local_rows) != windows[rank] and not (local_rows == 0 and windows[rank][0] == windows[rank][1]):
+        raise ValueError("rank %d holds rows [%d,%d) but shard_bounds(%d, %d) assigns %s"
+                         % (rank, row_offset, row_offset + local_rows, total_rows, world, windows[rank]))
+    per_rows = windows[0][1] - windows[0][0]                      # rows of a full shard: a multiple of 64
     nbytes = _lib.query("imp_modularity_workspace_bytes", total_rows, 1, n_tok1, n_tok2)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ws = _cached("modularity_ws", nbytes, dev)
     cu = torch.tensor([0, total_rows], dtype=torch.int32, device=dev)
     offs, sizes = (ctypes.c_size_t * 4)(), (ctypes.c_size_t * 4)()
     _lib.call("imp_modularity_sections", total_rows, 1, n_tok1, n_tok2, offs, sizes)
     _lib.call("imp_modularity_prepare", h_local, local_rows, int(row_offset), int(total_rows), cu, 1, chat, int(n_tok1),
               int(n_tok2), ws, _lib.stream_ptr())
-    # who owns which rows
-    mine = torch.tensor([row_offset, local_rows], dtype=torch.int64, device=dev)
-    allw = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(allw, mine, group=group)
-    windows = [tuple(int(v) for v in w.tolist()) for w in allw]
     ntile_total = (total_rows + 128 + 64 + 63) // 64
     tile_bytes = int(sizes[1]) // ntile_total
-    for r, (lo, n) in enumerate(windows):
-        if n == 0:
-            continue
-        src = dist.get_global_rank(group, r) if group is not None else r
-        xh = ws[int(offs[0]) + lo * 512: int(offs[0]) + (lo + n) * 512]
-        t0, t1 = lo // 64, (lo + n + 63) // 64
-        lf = ws[int(offs[1]) + t0 * tile_bytes: int(offs[1]) + t1 * tile_bytes]
-        dist.broadcast(xh, src=src, group=group)
-        dist.broadcast(lf, src=src, group=group)
+    _exchange_sections(ws, int(offs[0]), 512, windows, per_rows, rank, "xh_stage", group)          # x_hat rows, 512 B each
+    tile_windows = [(lo // 64, (hi + 63) // 64) for lo, hi in windows]
+    _exchange_sections(ws, int(offs[1]), tile_bytes, tile_windows, per_rows // 64, rank, "lf_stage", group)
     colsum = ws[int(offs[2]): int(offs[2]) + int(sizes[2])].view(torch.float32)
     flag = ws[int(offs[3]): int(offs[3]) + 4].view(torch.int32)
     dist.all_reduce(colsum, group=group)

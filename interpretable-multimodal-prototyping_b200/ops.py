@@ -146,9 +146,9 @@ class _ProtoFusionFn(torch.autograd.Function):
         lses = [saved[2 * k + 1] for k in range(nblk)]
         qts_c = [q.detach().contiguous() for q in qts]
         keep_scale = 1.0 / (1.0 - ctx.p_drop) if ctx.p_drop > 0 else 1.0
-        if ctx.p_drop > 0:   # the kernel keeps an element iff hash byte >= round(256 p): match its scale
-            thr = int(ctx.p_drop * 256.0 + 0.5)
-            keep_scale = 256.0 / (256.0 - thr) if thr else 1.0
+        if ctx.p_drop > 0:   # the kernel keeps an element iff its 16 hash bits >= round(65536 p): match its scale
+            thr = int(ctx.p_drop * 65536.0 + 0.5)
+            keep_scale = 65536.0 / (65536.0 - thr) if thr else 1.0
 
         outs, gouts = [c], [dc]          # running list of (tensor, cotangent) pairs of the token graph
         dpool: List[Optional[torch.Tensor]] = [None] * nblk

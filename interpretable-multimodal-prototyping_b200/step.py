@@ -100,21 +100,49 @@ class GraphedStep:
 
     def close(self) -> None:
         from . import _lib
-        _lib.call("imp_set_seed_offset", None)
+        if self._seed_word is not None:          # the library must not keep a pointer into a freed tensor
+            with torch.cuda.device(self._seed_word.device):
+                _lib.call("imp_set_seed_offset", None)
+            self._seed_word = None
         self.graph = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def allreduce_gradients(module: nn.Module, world_size: int) -> None:
     """Mean of the per-rank gradients in one flat bucket (NCCL over NVLink; gloo in CPU tests)."""
     import torch.distributed as dist
-    params = [p for p in module.parameters() if p.grad is not None]
-    if not params or world_size == 1:
+    if world_size == 1:
         return
-    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    # the bucket covers EVERY trainable parameter (missing gradients count as zero): the layout is then the same on
+    # all ranks even when one rank's batch had no omics and left the omic encoders without gradients
+    params = [p for p in module.parameters() if p.requires_grad]
+    if not params:
+        return
+    total = sum(p.numel() for p in params)
+    flat = getattr(module, "_imp_grad_bucket", None)
+    if flat is None or flat.numel() != total or flat.device != params[0].device:
+        flat = torch.empty(total, dtype=torch.float32, device=params[0].device)
+        module._imp_grad_bucket = flat
+    o = 0
+    for p in params:
+        n = p.numel()
+        if p.grad is None:
+            flat[o:o + n].zero_()
+        else:
+            flat[o:o + n].copy_(p.grad.reshape(-1))
+        o += n
     dist.all_reduce(flat)
     flat.div_(world_size)
     o = 0
     for p in params:
-        n = p.grad.numel()
-        p.grad.copy_(flat[o:o + n].view_as(p.grad))
+        n = p.numel()
+        if p.grad is None:
+            p.grad = flat[o:o + n].view_as(p).clone()
+        else:
+            p.grad.copy_(flat[o:o + n].view_as(p.grad))
         o += n

@@ -148,7 +148,7 @@ def modularity_literal(c: torch.Tensor, x: torch.Tensor, temp: float = 0.1) -> t
 
 
 def modularity(c: torch.Tensor, x: torch.Tensor, temp: float = 0.1, chunk: int = 512,
-               want_grad: bool = True, acc_dtype: torch.dtype = torch.float64):
+               want_grad: bool = True, acc_dtype: torch.dtype = torch.float64, gram_bf16: bool = False):
     """Chunked modularity loss and its gradient wrt c.
 
     loss = -100 * [ sum_ij A_ij delta_ij / e  -  sum_ij d_i d_j delta_ij / e^2 ],
@@ -160,29 +160,32 @@ def modularity(c: torch.Tensor, x: torch.Tensor, temp: float = 0.1, chunk: int =
     """
     x = x.detach()
     n = x.shape[0]
+    dev = x.device                       # runs wherever its inputs live (tests use fp64 on the GPU for 16k / 120k bags)
     cw = c.detach().clone().requires_grad_(want_grad)
     cm = cluster_assignment(x, cw)                                  # (N,P) with graph to cw
     cmd = cm.detach()
     xh = x / x.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    if gram_bf16:                        # the device keeps the Gram operand x_hat in bf16: same rounding point here
+        xh = xh.to(torch.bfloat16).to(x.dtype)
     # pass 1: degrees
-    d = torch.zeros(n, dtype=acc_dtype)
+    d = torch.zeros(n, dtype=acc_dtype, device=dev)
     for i0 in range(0, n, chunk):
         a = torch.relu(xh[i0:i0 + chunk] @ xh.t())
-        r = torch.arange(i0, min(i0 + chunk, n))
+        r = torch.arange(i0, min(i0 + chunk, n), device=dev)
         a[r - i0, r] = 0
         d[i0:i0 + chunk] = a.sum(dim=1, dtype=acc_dtype)
     e = d.sum()
     # pass 2: the two traces and dL/dC
-    s1 = torch.zeros((), dtype=acc_dtype)
-    s2 = torch.zeros((), dtype=acc_dtype)
-    dcm = torch.zeros(cmd.shape, dtype=acc_dtype)
+    s1 = torch.zeros((), dtype=acc_dtype, device=dev)
+    s2 = torch.zeros((), dtype=acc_dtype, device=dev)
+    dcm = torch.zeros(cmd.shape, dtype=acc_dtype, device=dev)
     for i0 in range(0, n, chunk):
         ci = cmd[i0:i0 + chunk]                                      # (m,P)
         a = torch.relu(xh[i0:i0 + chunk] @ xh.t())
-        r = torch.arange(i0, min(i0 + chunk, n))
+        r = torch.arange(i0, min(i0 + chunk, n), device=dev)
         a[r - i0, r] = 0
-        u = torch.full((ci.shape[0], n), -1.0, dtype=cmd.dtype)
-        arg = torch.zeros((ci.shape[0], n), dtype=torch.long)
+        u = torch.full((ci.shape[0], n), -1.0, dtype=cmd.dtype, device=dev)
+        arg = torch.zeros((ci.shape[0], n), dtype=torch.long, device=dev)
         for p in range(cmd.shape[1]):                                # first max wins (torch.max)
             v = ci[:, p:p + 1] * cmd[None, :, p]
             better = v > u
@@ -195,9 +198,8 @@ def modularity(c: torch.Tensor, x: torch.Tensor, temp: float = 0.1, chunk: int =
         if want_grad:
             g = -100.0 * (a.to(acc_dtype) / e - dd / (e * e))
             wgt = 2.0 * g * (1.0 - delta * delta) / temp            # (m,N)
-            cj = cmd.to(acc_dtype).t()                               # (P,N)
-            picked = torch.gather(cj.t()[None].expand(ci.shape[0], -1, -1), 2,
-                                  arg[:, :, None]).squeeze(2)        # C_j,p*  (m,N)
+            cols = torch.arange(n, device=dev)[None, :].expand(ci.shape[0], -1)
+            picked = cmd.to(acc_dtype)[cols, arg]                    # C_j,p*  (m,N)
             dcm[i0:i0 + chunk].scatter_add_(1, arg.reshape(ci.shape[0], -1), wgt * picked)
     loss = -100.0 * (s1 / e - s2 / (e * e))
     dc = None

@@ -79,3 +79,32 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "wsi_bags_per_s_fwd_bwd" and d["unit"] == "bags/s"
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_packed_wire_format_round_trips_the_reference_layout():
+    """wire.collate_packed on samples shaped like DatasetWrapper_UMEML.__getitem__ (data_manager.py:395-403):
+    valid rows only, bf16, offsets; identical (after the bf16 rounding the kernels apply anyway) to the padded
+    fp32 reference layout it replaces."""
+    from imp_b200 import wire
+    g = torch.Generator().manual_seed(0)
+    lens = [37, 1, 300]
+    samples = []
+    for i, n in enumerate(lens):
+        bag = torch.randn(n, 512, generator=g)
+        samples.append({"img": wire.pad_bag(bag, 512), "mol": torch.rand(3354, generator=g), "label": torch.tensor(i % 4),
+                        "survival_month": torch.tensor(12.0 + i), "censorship": torch.tensor(i % 2),
+                        "patient_id": "TCGA-%02d" % i, "index": i})
+        assert wire.bag_rows(samples[-1]["img"]) == n == O.bag_length(samples[-1]["img"])
+    batch = wire.collate_packed(samples)
+    assert batch["x_packed"].dtype == torch.bfloat16 and batch["x_packed"].shape == (sum(lens), 512)
+    assert batch["cu_seqlens"].tolist() == [0, 37, 38, 338] and batch["max_len"] == 300
+    assert batch["omic"].shape == (3, 3354) and batch["patient_id"] == ["TCGA-00", "TCGA-01", "TCGA-02"]
+    img = wire.unpack_to_reference_layout(batch, 512)
+    ref = torch.stack([s["img"] for s in samples])
+    valid = ref != wire.SENTINEL
+    assert torch.equal(valid, img != wire.SENTINEL)
+    assert torch.equal(img[valid], ref[valid].bfloat16().float())
+    means = wire.omic_means([{"mol": batch["mol"][:2]}, {"mol": batch["mol"][2:]}])
+    assert torch.allclose(means, batch["mol"].mean(0), atol=1e-6)          # trainer.py:286-291
+    big = wire.pad_bag(torch.randn(20, 512, generator=g), 16)              # >= target rows: returned unpadded
+    assert big.shape == (20, 512) and wire.bag_rows(big) == 20

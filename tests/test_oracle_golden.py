@@ -101,3 +101,21 @@ def test_distance_and_argmin_match_reference():
     z = load("distance_N96_K8.npz")
     a = O.kmeans_assign(z["x"], z["mu"])
     assert torch.equal(a.long(), z["argmin"].long())
+
+
+def test_rounding_model_without_roundings_is_the_oracle():
+    """oracle/rounding_model.py with no rounding point switched on must reproduce hot_path_step (and therefore
+    the executed reference through the chain fixture); with all six on it must stay within the bf16 floor."""
+    from oracle import rounding_model as R
+    z = load("chain_P16_N384.npz")
+    params = make_params(int(z["param_seed"]))
+    exact = O.hot_path_step([z["x"][0].double()], {k: v.double() for k, v in params.items()}, z["p_proto"][0].double(),
+                            with_modularity=False, grad_seed=z["cot"].double())
+    plain = R.hot_path_step_rounded([z["x"][0]], params, z["p_proto"][0], z["cot"], points=())
+    assert rel(plain["c"], exact["c"]) < 1e-12
+    for k in exact["grads"]:
+        assert rel(plain["grads"][k], exact["grads"][k]) < 1e-10, k
+    rounded = R.hot_path_step_rounded([z["x"][0]], params, z["p_proto"][0], z["cot"])
+    assert rel(rounded["c"], exact["c"]) < 1e-3
+    worst = max(rel(rounded["grads"][k], exact["grads"][k]) for k in exact["grads"])
+    assert 1e-5 < worst < 1e-2, worst

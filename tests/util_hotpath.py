@@ -59,3 +59,27 @@ def make_omic_params(seed=0):
         out["omic_net.%d.0.weight" % k] = (torch.rand(256, s, generator=g) * 2 - 1) / math.sqrt(s)
         out["omic_net.%d.0.bias" % k] = 0.05 * torch.randn(256, generator=g)
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# parity ledger: every GPU parity test appends its measured errors here so that the numbers behind
+# the asserts are visible (gpurun_out/r02_parity.jsonl on the GPU box -> profiles/r02_parity.md)
+# --------------------------------------------------------------------------------------------
+def record(test: str, quantity: str, err: float, tol: float, against: str, note: str = ""):
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "r02_parity.jsonl"), "a") as f:
+            f.write(json.dumps({"test": test, "quantity": quantity, "err": float(err), "tol": float(tol),
+                                "against": against, "note": note}) + "\n")
+    except OSError:
+        pass
+    return err
+
+
+def check(test: str, quantity: str, err: float, tol: float, against: str, note: str = ""):
+    record(test, quantity, err, tol, against, note)
+    assert err <= tol, "%s / %s: %.3e > %.1e (vs %s)" % (test, quantity, err, tol, against)
