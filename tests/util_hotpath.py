@@ -83,3 +83,19 @@ def record(test: str, quantity: str, err: float, tol: float, against: str, note:
 def check(test: str, quantity: str, err: float, tol: float, against: str, note: str = ""):
     record(test, quantity, err, tol, against, note)
     assert err <= tol, "%s / %s: %.3e > %.1e (vs %s)" % (test, quantity, err, tol, against)
+
+
+class Ledger:
+    """Collects the checks of one test so that EVERY measured error reaches the parity ledger before the first
+    failing one raises."""
+
+    def __init__(self, test: str):
+        self.test, self.bad = test, []
+
+    def add(self, quantity: str, err: float, tol: float, against: str, note: str = ""):
+        record(self.test, quantity, err, tol, against, note)
+        if not err <= tol:
+            self.bad.append("%s: %.3e > %.1e (vs %s)" % (quantity, err, tol, against))
+
+    def assert_ok(self):
+        assert not self.bad, "%s: %s" % (self.test, "; ".join(self.bad))
