@@ -114,8 +114,9 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
   uint64_t* sempty = bars + 6;      // [2] 4 warps -> MMA1 (S in registers)
   uint64_t* wfull = bars + 8;       // [2] 4 warps -> MMA2 (w written, acc rescaled)
   uint64_t* wempty = bars + 10;     // [2] MMA2 retired -> epilogue (w buffer reusable)
-  uint64_t* accdone = bars + 12;    // MMA2 of a tile retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* accdone = bars + 12;    // MMA2 of a tile retired (slow path: at most one phase behind, see there)
+  uint64_t* alldone = bars + 13;    // MMA2 of the CTA's LAST tile retired (single phase)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int b = blockIdx.y, split = blockIdx.x;
   const int row_begin = __ldg(p.cu + b), row_end = __ldg(p.cu + b + 1);
@@ -138,6 +139,7 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 4); mbar_init(&wfull[i], 4); mbar_init(&wempty[i], 1); }
     mbar_init(accdone, 1);
+    mbar_init(alldone, 1);
     mbar_fence_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, 512);
@@ -236,6 +238,7 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
         umma_commit(&empty[stage]);
         umma_commit(&wempty[wb]);
         umma_commit(accdone);
+        if (i == ntiles - 1) umma_commit(alldone);
       }
     }
   } else {
@@ -282,7 +285,10 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
           }
           bar_sync(2, 128);
           if (i > 0) {
-            mbar_wait(accdone, (i - 1) & 1);                            // MMA2 of tile i-1 (and everything before) retired
+            // MMA2 of tile i-1 retired.  S of tile i exists, so MMA1(i) and everything issued before it, MMA2(i-2)
+            // included, has completed (the tensor pipe retires in issue order): accdone has seen i-1 or i commits and
+            // the parity of phase i-1 is unambiguous.
+            mbar_wait(accdone, (i - 1) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int r = 0; r < 3; ++r) {                               // acc half 0, acc half 1, l
@@ -334,7 +340,8 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
       if (lane == 0) mbar_arrive(&wfull[wb]);
     }
     // ---- write the partial state: acc^T lives as [feature lane][prototype column] ----
-    mbar_wait(accdone, (ntiles - 1) & 1);
+    // the epilogue can run two MMA2 commits ahead here, which a parity wait on accdone cannot tell apart
+    mbar_wait(alldone, 0);
     tc_fence_after();
 #pragma unroll 1
     for (int hf = 0; hf < 2; ++hf) {

@@ -1,0 +1,176 @@
+"""Token-level tail of ``UMEML_GAN``: everything that works on the <= 40 tokens per slide
+after the prototype-fusion hot path.  Batched torch, fixed shapes, no host synchronisation.
+
+Reference (medmm/modeling/...), restated -- module and parameter names are the ``state_dict`` contract and are
+kept; the arithmetic is re-derived in batched form:
+  * ``NystromAttention``            ops/attention.py:46-161 (+ ``moore_penrose_iter_pinv`` ops/utils.py:116-131)
+  * ``TransLayer``                  ops/blocks.py:252-268
+  * ``Block``                       models/umeml_gan.py:86-96
+  * ``BottleneckAttentionBlock``    models/umeml_gan.py:100-229 -- the reference fills a 7 x 7 similarity matrix with
+    49 ``.item()`` round trips per slide (:126-129), sorts it on the host and pairs greedily (:174-186), then
+    rebuilds the token list in Python (:188-220), twice per forward.  Here the greedy pairing is three masked
+    arg-max steps on the device for the whole batch and the re-ordering is two gathers.
+  * ``Generator`` / ``Discriminator``   models/umeml_gan.py:25-62
+"""
+from __future__ import annotations
+
+import math
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def iterative_pinv(a: torch.Tensor, iters: int = 6) -> torch.Tensor:
+    """Newton-Schulz style pseudo-inverse used by the Nystrom layers (ops/utils.py:116-131).  The initial scale is
+    1 / (max column abs-sum x max row abs-sum) taken over the WHOLE tensor (all slides and heads together), as in
+    the reference (``torch.max(col) * torch.max(row)`` :121)."""
+    absa = a.abs()
+    z = a.transpose(-1, -2) / (absa.sum(dim=-1).max() * absa.sum(dim=-2).max())
+    eye = torch.eye(a.shape[-1], device=a.device, dtype=a.dtype)
+    for _ in range(iters):
+        az = a @ z
+        z = 0.25 * z @ (13 * eye - az @ (15 * eye - az @ (7 * eye - az)))
+    return z
+
+
+class NystromAttention(nn.Module):
+    def __init__(self, dim, dim_head=64, heads=8, num_landmarks=256, pinv_iterations=6, residual=True,
+                 residual_conv_kernel=33, eps=1e-8, dropout=0.0):
+        super().__init__()
+        inner = heads * dim_head
+        self.eps, self.heads, self.num_landmarks, self.pinv_iterations = eps, heads, num_landmarks, pinv_iterations
+        self.scale = dim_head ** -0.5
+        self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(dropout))
+        self.residual = residual
+        if residual:
+            self.res_conv = nn.Conv2d(heads, heads, (residual_conv_kernel, 1), padding=(residual_conv_kernel // 2, 0),
+                                      groups=heads, bias=False)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        b, n, _ = x.shape
+        h, m = self.heads, self.num_landmarks
+        pad = (m - n % m) % m                                   # zero tokens in FRONT (attention.py:79-81)
+        if pad:
+            x = F.pad(x, (0, 0, pad, 0))
+        npad = n + pad
+        qkv = self.to_qkv(x).view(b, npad, 3, h, -1).permute(2, 0, 3, 1, 4)     # (3, b, h, npad, d)
+        q, k, v = qkv[0] * self.scale, qkv[1], qkv[2]
+        grp = math.ceil(n / m)                                  # tokens per landmark (:97-101)
+        ql = q.reshape(b, h, npad // grp, grp, -1).sum(dim=3) / grp
+        kl = k.reshape(b, h, npad // grp, grp, -1).sum(dim=3) / grp
+        a1 = torch.softmax(q @ kl.transpose(-1, -2), dim=-1)
+        a2 = torch.softmax(ql @ kl.transpose(-1, -2), dim=-1)
+        a3 = torch.softmax(ql @ k.transpose(-1, -2), dim=-1)
+        out = (a1 @ iterative_pinv(a2, self.pinv_iterations)) @ (a3 @ v)
+        if self.residual:
+            out = out + self.res_conv(v)
+        out = self.to_out(out.transpose(1, 2).reshape(b, npad, -1))
+        return out[:, -n:]
+
+
+class TransLayer(nn.Module):
+    def __init__(self, norm_layer=nn.LayerNorm, dim=512):
+        super().__init__()
+        self.norm = norm_layer(dim)
+        self.attn = NystromAttention(dim=dim, dim_head=dim // 8, heads=8, num_landmarks=dim // 2, pinv_iterations=6,
+                                     residual=True, dropout=0.1)
+
+    def forward(self, x):
+        return x + self.attn(self.norm(x))
+
+
+class Block(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.attn = TransLayer(dim=dim)
+
+    def forward(self, x):
+        return self.attn(x)
+
+
+def greedy_pairs(sim: torch.Tensor, k: int = 3) -> Tuple[torch.Tensor, torch.Tensor]:
+    """sim (B, Lp, Lo) -> (i_p (B,k), i_o (B,k)): the k best pairs with distinct rows and columns, best first.
+    Equivalent to the reference's scan of the descending-sorted entries that skips used rows/columns
+    (umeml_gan.py:174-186): the next accepted entry is always the arg-max over the rows and columns still free."""
+    b, lp, lo = sim.shape
+    work = sim.clone()
+    ips, ios = [], []
+    neg = torch.finfo(sim.dtype).min
+    for _ in range(k):
+        flat = work.reshape(b, -1).argmax(dim=1)
+        ip, io = flat // lo, flat % lo
+        ips.append(ip); ios.append(io)
+        work = work.masked_fill(F.one_hot(ip, lp).bool()[:, :, None] | F.one_hot(io, lo).bool()[:, None, :], neg)
+    return torch.stack(ips, dim=1), torch.stack(ios, dim=1)
+
+
+def _remaining(tokens: torch.Tensor, picked: torch.Tensor) -> torch.Tensor:
+    """tokens (B,L,D) without the rows ``picked`` (B,k), original order kept (umeml_gan.py:200-217)."""
+    b, l, d = tokens.shape
+    taken = F.one_hot(picked, l).sum(dim=1)                                      # (B,L) 0/1
+    order = torch.argsort(taken * l + torch.arange(l, device=tokens.device)[None, :], dim=1)
+    keep = order[:, : l - picked.shape[1]]
+    return torch.gather(tokens, 1, keep[:, :, None].expand(-1, -1, d))
+
+
+class BottleneckAttentionBlock(nn.Module):
+    def __init__(self, dim: int = 256, n_reg: int = 2):
+        super().__init__()
+        self.bottle_tokens = nn.Parameter(torch.empty(1, n_reg, dim).uniform_())
+        self.encoders = nn.ModuleList([Block(dim=dim) for _ in range(2)])
+        self.linear_p = nn.Linear(dim, dim)          # the reference attaches these from UMEML_GAN.__init__ (:307-308)
+        self.linear_o = nn.Linear(dim, dim)
+
+    def forward(self, x_path: torch.Tensor, x_omic: torch.Tensor, patient_id=None):
+        b, path_len, d = x_path.shape
+        token_len = self.bottle_tokens.shape[1]
+        pn = x_path / x_path.norm(dim=-1, keepdim=True).clamp_min(1e-8)          # F.cosine_similarity, eps 1e-8 (:129)
+        on = x_omic / x_omic.norm(dim=-1, keepdim=True).clamp_min(1e-8)
+        ip, io = greedy_pairs((pn @ on.transpose(1, 2)).detach(), 3)
+        sel_p = torch.gather(x_path, 1, ip[:, :, None].expand(-1, -1, d))
+        sel_o = torch.gather(x_omic, 1, io[:, :, None].expand(-1, -1, d))
+        ks = self.linear_p(sel_p) + self.linear_o(sel_o)                         # :194, in pairing order
+        x = torch.cat([ks, _remaining(x_path, ip), self.bottle_tokens.expand(b, -1, -1), _remaining(x_omic, io)], dim=1)
+        for blk in self.encoders:
+            x = blk(x)
+        # the reference slices with the ORIGINAL lengths although three tokens per modality were merged (:227-228)
+        t_path, f_path = x[:, :1], x[:, 1:path_len]
+        t_omic, f_omic = x[:, path_len + token_len: path_len + token_len + 1], x[:, path_len + token_len + 1:]
+        return t_path, f_path, t_omic, f_omic
+
+
+class Generator(nn.Module):
+    def __init__(self, input_dim, output_dim):
+        super().__init__()
+        self.input_dim, self.output_dim = tuple(input_dim), tuple(output_dim)
+        self.net = nn.Sequential(nn.Linear(input_dim[0] * input_dim[1], 1024), nn.ReLU(),
+                                 nn.Linear(1024, output_dim[0] * output_dim[1]), nn.Softplus())
+
+    def forward(self, x):
+        if tuple(x.shape[-2:]) != self.input_dim:
+            raise ValueError(f"Expected input shape (-2 dimensions): {self.input_dim}, but got: {tuple(x.shape[-2:])}")
+        return self.net(x.reshape(x.shape[0], -1)).view(x.shape[0], *self.output_dim)
+
+
+class Discriminator(nn.Module):
+    def __init__(self, input_shape):
+        super().__init__()
+        self.layers = nn.Sequential(nn.Linear(input_shape[0] * input_shape[1], 256), nn.ReLU(), nn.Linear(256, 1), nn.Sigmoid())
+
+    def forward(self, x):
+        return self.layers(x.reshape(x.shape[0], -1))
+
+
+def transform_importance(x: torch.Tensor) -> torch.Tensor:
+    """per-sample min-max to [0.5, 1] (umeml_gan.py:689-694)"""
+    lo, hi = x.min(dim=1, keepdim=True)[0], x.max(dim=1, keepdim=True)[0]
+    return 0.5 + 0.5 * (x - lo) / (hi - lo + 1e-8)
+
+
+def transform_importance_to_half_one_point_five(x: torch.Tensor) -> torch.Tensor:
+    """per-sample min-max to [0.5, 1.5] (umeml_gan.py:696-702)"""
+    lo, hi = x.min(dim=1, keepdim=True)[0], x.max(dim=1, keepdim=True)[0]
+    return 0.5 + (x - lo) / (hi - lo + 1e-8)
