@@ -475,8 +475,9 @@ struct DzParams {
   const float* lse[2];     // (B,P)
   const float* delta[2];   // (B,P)
   float* part_db;          // (B*nsplit, 256) or null
+  float* part_dq;          // (B, nsplit, PP, 256) partial dq~ of block `dq_block`, or null
   bf16* dz;                // (R,256)
-  int P, nsplit, tiles_per_split;
+  int P, nsplit, tiles_per_split, dq_block;
   int relu_mask;
   float keep_scale;
 };
@@ -516,6 +517,8 @@ pool_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const DzParams p) {
   if (ntiles == 0) {
     if (p.part_db)
       for (int i = threadIdx.x; i < kD; i += kZThreads) p.part_db[((size_t)b * p.nsplit + split) * kD + i] = 0.f;
+    if (p.part_dq)
+      for (int i = threadIdx.x; i < PP * kD; i += kZThreads) p.part_dq[((size_t)b * p.nsplit + split) * PP * kD + i] = 0.f;
     return;
   }
   if (warp == 8 && lane == 0) {
@@ -548,7 +551,10 @@ pool_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const DzParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_s = tmem_base, tm_d = tmem_base + 128;
+  const uint32_t tm_s = tmem_base, tm_d = tmem_base + 128, tm_q = tmem_base + 384;   // S | dh | dq~^T (2 x 64 columns)
+  // dq~ of block p.dq_block rides along: dq~^T[f][p] += sum_n h[n][f] dS[n][p] with A = h^T (the tile read MN-major) and
+  // B = the 64-column box of E that holds dS of that block (the same image MMA2 reads K-major, here MN-major)
+  const int dq_col = p.dq_block * 2 * PP;
 
   if (warp == 8) {
     // ------------------------------ TMA producer ------------------------------
@@ -568,7 +574,9 @@ pool_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const DzParams p) {
     if (lane == 0) {
       constexpr uint32_t idesc1 = umma_idesc_bf16(kZM, NCOL, 0, 0);
       constexpr uint32_t idesc2 = umma_idesc_bf16(kZM, kD, 0, 1);
+      constexpr uint32_t idesc3 = umma_idesc_bf16(128, 64, 1, 1);
       const uint32_t sg = smem_u32(s_g), se = smem_u32(s_e);
+      const bool with_dq = p.part_dq != nullptr;
       for (int i = 0; i < ntiles; ++i) {
         const int stage = i & 1;
         const uint32_t sh = smem_u32(tiles + (size_t)stage * kZTile);
@@ -585,6 +593,18 @@ pool_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const DzParams p) {
         mbar_wait_idle(efull, i & 1);
         mbar_wait_idle(dempty, (i & 1) ^ 1);
         tc_fence_after();
+        if (with_dq) {                            // before MMA2: its commit (dfull) lets epilogue 2 overwrite the h tile
+          const uint32_t sebox = se + (dq_col >> 6) * (kZM * 128);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+            for (int k = 0; k < kZM / 16; ++k) {
+              const uint64_t ad = umma_desc_sw128(sh + hf * 2 * (kZM * 128) + k * 2048, kZM * 128, 1024);
+              const uint64_t bd = umma_desc_sw128(sebox + k * 2048, kZM * 128, 1024);
+              umma_f16(tm_q + hf * 64, ad, bd, idesc3, (i | k) != 0);
+            }
+          }
+        }
 #pragma unroll
         for (int k = 0; k < NCOL / 16; ++k) {     // dh = E G, K = NCOL stacked prototype rows
           const uint64_t ad = umma_desc_sw128(se + (k >> 2) * (kZM * 128) + (k & 3) * 32, 0, 1024);
@@ -680,6 +700,18 @@ pool_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const DzParams p) {
       if (lane == 0) mbar_arrive(&empty[stage]);
     }
     if (p.part_db) p.part_db[((size_t)b * p.nsplit + split) * kD + threadIdx.x] = dbacc;
+    if (p.part_dq) {                               // every MMA of the CTA has retired (dfull of the last tile was waited for)
+      float* out_dq = p.part_dq + ((size_t)b * p.nsplit + split) * PP * kD;
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < PP; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tm_q + lane_addr + hf * 64 + (dq_col & 63) + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) out_dq[(size_t)(c0 + e) * kD + hf * 128 + n] = __uint_as_float(v[e]);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -841,7 +873,7 @@ size_t pool_bwd_workspace_bytes(int B, int max_len, int P) {
   dz_split_plan(max_len, B, &nz, &tz);
   int nt, tt;
   pool_tc_split_plan(max_len, B, &nt, &tt);
-  const size_t dq_part = std::max((size_t)B * ns * PP * kD, (size_t)B * nt * pool_tc_pad(P) * kD);
+  const size_t dq_part = std::max(std::max((size_t)B * ns * PP * kD, (size_t)B * nt * pool_tc_pad(P) * kD), (size_t)B * nz * PP * kD);
   return (dq_part + (size_t)B * nz * kD) * sizeof(float);
 }
 
@@ -878,9 +910,17 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
     int nt, tt;
     pool_tc_split_plan(max_len, B, &nt, &tt);
     dq_part_elems = std::max(dq_part_elems, (size_t)B * nt * pool_tc_pad(P) * kD);
+    int nz0, tz0;
+    dz_split_plan(max_len, B, &nz0, &tz0);
+    dq_part_elems = std::max(dq_part_elems, (size_t)B * nz0 * PP * kD);
     if (!use_legacy_pool()) { dq_ns = nt; dq_pp = pool_tc_pad(P); }
   }
-  if (!use_legacy_pool()) {
+  const bool fused_dq = dz != nullptr && !use_legacy_pool();     // the dz kernel forms dq~ of `dq_block` on the way
+  if (fused_dq) {
+    int nz0, tz0;
+    dz_split_plan(max_len, B, &nz0, &tz0);
+    dq_ns = nz0; dq_pp = PP;
+  } else if (!use_legacy_pool()) {
     int nt, tt;
     pool_tc_split_plan(max_len, B, &nt, &tt);
     rc = launch_pool_tc_dq(h, total_rows, cu, B, qt[dq_block], qt_stride[dq_block], dpool[dq_block], (long long)P * kD,
@@ -908,6 +948,8 @@ int launch_pool_bwd(const bf16* h, int total_rows, const int* cu, int B, int max
       z.lse[k] = p.lse[k]; z.delta[k] = p.delta[k];
     }
     z.part_db = db1 ? workspace + dq_part_elems : nullptr;
+    z.part_dq = fused_dq ? p.part_dq : nullptr;
+    z.dq_block = dq_block;
     CUtensorMap tmz;
     if ((rc = imp_make_tmap_2d(&tmz, h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, total_rows, kD * 2, 64, kZM,
                                CU_TENSOR_MAP_SWIZZLE_128B))) return rc;

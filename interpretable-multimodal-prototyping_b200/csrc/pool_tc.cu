@@ -11,8 +11,8 @@
 //         -> bf16, written as the MN-major B operand of MMA2 ([128 rows n][64 p], one 128-byte row per patch)
 //   MMA2  acc[f][p]   += sum_n h[n][f] w[n][p]           M 128 (features, two halves), N 64, K 128 (patch rows);
 //                                                        A = the SAME h tile read MN-major (h^T), B = w
-//         fwd only:  l[.][p] += sum_n 1 * w[n][p]         A = a tile of ones: the softmax normaliser comes out of the
-//                                                        tensor core from the same bf16-rounded weights, no cross-thread sum
+//         fwd only:  l[p] += sum_n w[n][p]                from the same bf16-rounded weights: a 31-shuffle transposing
+//                                                        reduction per warp leaves column p's sum in lane p
 // The P x 256 results live transposed in TMEM (lane = feature, column = prototype): 2 x 64 columns instead of
 // 256 x 128 lanes of which only P would be used, and a rescale touches 64 columns per thread.
 //
@@ -24,8 +24,11 @@
 // maximum over the bag's earlier tiles).  The partial state a CTA leaves is (m_p, l_p, acc_p) like the mma.sync
 // kernel it replaces, merged across the CTAs of a bag by pool_merge / reduce_dq (pool.cu).
 //
-// Warps: 0-3 epilogue, 4 TMA producer, 5 MMA issuer.  MMA1 of tile t+1 is issued before MMA2 of tile t (S is double
-// buffered in TMEM), so the tensor pipe works on the next scores while the epilogue turns the current ones into w.
+// Warps: 0-3 epilogue, 4 TMA producer, 5 MMA issuer.  The issuer polls its barriers instead of waiting in a fixed
+// order: MMA1 of tile t+1 goes out as soon as its h tile has landed (S is double buffered in TMEM), MMA2 of tile t as
+// soon as w is written -- a blocking wait for the NEXT tile's load in front of MMA2(t) kept the stage of tile t, and with
+// it the load of tile t+2, hostage (one load in flight per SM: 2.9 us per tile, first version).  The forward with
+// P <= 32 runs three stages of h (192 KB).
 #include "common.cuh"
 #include "launchers.h"
 
@@ -35,7 +38,6 @@ constexpr int kD = 256;
 constexpr int kTM = 128;                        // patch rows per tile
 constexpr int kTile = kTM * kD * 2;             // 64 KB: four [128 rows][64 feats] boxes
 constexpr int kBox = kTM * 128;                 // 16 KB
-constexpr int kStages = 2;
 constexpr int kThreads = 6 * 32;
 constexpr int kWBox = kTM * 128;                // one w buffer: [128 rows][64 p] bf16
 constexpr float kLog2e = 1.4426950408889634f;
@@ -88,35 +90,34 @@ struct PoolTcParams {
 template <int PP, int MODE>
 struct Cfg {
   static constexpr int N1 = MODE == MODE_FWD ? PP : 2 * PP;           // columns of S
-  static constexpr int NBUF = (MODE == MODE_DQ && PP == 64) ? 1 : 2;  // w buffers (shared memory budget)
-  static constexpr size_t smem = 1024 + (size_t)kStages * kTile + (size_t)N1 * 512 + (size_t)NBUF * kWBox +
-                                 (MODE == MODE_FWD ? kBox : 0) + (4 + 2 + 2) * 64 * 4 + 256;
+  static constexpr int STAGES = (MODE == MODE_FWD && PP == 32) ? 3 : 2;   // h tiles in flight (shared memory budget)
+  static constexpr int NBUF = (STAGES == 3 || (MODE == MODE_DQ && PP == 64)) ? 1 : 2;   // w buffers
+  static constexpr size_t smem = 1024 + (size_t)STAGES * kTile + (size_t)N1 * 512 + (size_t)NBUF * kWBox + 6 * 64 * 4 + 192;
 };
 
 template <int PP, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
   using C = Cfg<PP, MODE>;
-  constexpr int N1 = C::N1, NBUF = C::NBUF;
+  constexpr int N1 = C::N1, NBUF = C::NBUF, kStages = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* tiles = smem;                                       // kStages h tiles
   uint8_t* s_g = tiles + (size_t)kStages * kTile;              // G: 4 boxes [N1][64], box stride N1*128
   uint8_t* s_w = s_g + (size_t)N1 * 512;                       // NBUF boxes [128][64]
-  uint8_t* s_ones = s_w + (size_t)NBUF * kWBox;                // fwd: [128][64] of 1.0
-  float* s_wmax = reinterpret_cast<float*>(s_ones + (MODE == MODE_FWD ? kBox : 0));   // [4][64]
+  float* s_wmax = reinterpret_cast<float*>(s_w + (size_t)NBUF * kWBox);   // [4][64]
   float* s_m = s_wmax + 4 * 64;                                // [64] running maximum (log2 units) | dq: lse * log2e
   float* s_alpha = s_m + 64;                                   // [64] rescale factors            | dq: delta
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_alpha + 64 + 64);
-  uint64_t* full = bars;            // [kStages] TMA -> MMA1
-  uint64_t* empty = bars + 2;       // [kStages] MMA2 retired -> TMA
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_alpha + 64);
+  uint64_t* full = bars + 14;       // [kStages] TMA -> MMA1
+  uint64_t* empty = bars + 17;      // [kStages] MMA2 retired -> TMA
   uint64_t* sfull = bars + 4;       // [2] MMA1 -> epilogue
   uint64_t* sempty = bars + 6;      // [2] 4 warps -> MMA1 (S in registers)
   uint64_t* wfull = bars + 8;       // [2] 4 warps -> MMA2 (w written, acc rescaled)
   uint64_t* wempty = bars + 10;     // [2] MMA2 retired -> epilogue (w buffer reusable)
   uint64_t* accdone = bars + 12;    // MMA2 of a tile retired (slow path: at most one phase behind, see there)
   uint64_t* alldone = bars + 13;    // MMA2 of the CTA's LAST tile retired (single phase)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int b = blockIdx.y, split = blockIdx.x;
   const int row_begin = __ldg(p.cu + b), row_end = __ldg(p.cu + b + 1);
@@ -158,8 +159,6 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
   }
   for (int i = threadIdx.x; i < NBUF * kWBox / 16; i += kThreads) reinterpret_cast<uint4*>(s_w)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (MODE == MODE_FWD) {
-    for (int i = threadIdx.x; i < kBox / 16; i += kThreads)
-      reinterpret_cast<uint4*>(s_ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     for (int i = threadIdx.x; i < 64; i += kThreads) { s_m[i] = -INFINITY; s_alpha[i] = 0.f; }
   } else {
     for (int i = threadIdx.x; i < 64; i += kThreads) {
@@ -173,7 +172,7 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_s0 = tmem_base, tm_acc = tmem_base + 256, tm_l = tmem_base + 384;   // S: 2 x N1 <= 256 columns
+  const uint32_t tm_s0 = tmem_base, tm_acc = tmem_base + 256;   // S: 2 x N1 <= 256 columns; acc: 2 x 64
 
   if (warp == 4) {
     // ------------------------------ TMA producer ------------------------------
@@ -193,52 +192,47 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
     if (lane == 0) {
       constexpr uint32_t idesc1 = umma_idesc_bf16(kTM, N1, 0, 0);
       constexpr uint32_t idesc2 = umma_idesc_bf16(128, 64, 1, 1);       // A = h^T (MN-major), B = w (MN-major)
-      constexpr uint32_t idescl = umma_idesc_bf16(128, 64, 0, 1);       // A = ones (K-major), B = w (MN-major)
-      const uint32_t sg = smem_u32(s_g), sw = smem_u32(s_w), so = smem_u32(s_ones);
-      auto mma1 = [&](int j) {
-        const int stage = j % kStages, buf = j & 1;
-        mbar_wait_idle(&full[stage], (j / kStages) & 1);
-        mbar_wait_idle(&sempty[buf], ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t sh = smem_u32(tiles + (size_t)stage * kTile);
+      const uint32_t sg = smem_u32(s_g), sw = smem_u32(s_w);
+      int next1 = 0, next2 = 0;                                           // next tile for MMA1 / MMA2
+      while (next2 < ntiles) {
+        // MMA1(j): its h tile has landed and the S buffer was read.  Never more than one tile ahead of the MMA2 that
+        // was ISSUED last (the slow path's accdone parity argument needs MMA2(j-2) in front of MMA1(j)).
+        if (next1 < ntiles && next1 <= next2 + 1 && mbar_test(&full[next1 % kStages], (next1 / kStages) & 1) &&
+            mbar_test(&sempty[next1 & 1], ((next1 >> 1) & 1) ^ 1)) {
+          const int j = next1++, stage = j % kStages, buf = j & 1;
+          tc_fence_after();
+          const uint32_t sh = smem_u32(tiles + (size_t)stage * kTile);
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) {
-          const uint64_t ad = umma_desc_sw128(sh + (k >> 2) * kBox + (k & 3) * 32, 0, 1024);
-          const uint64_t bd = umma_desc_sw128(sg + (k >> 2) * (N1 * 128) + (k & 3) * 32, 0, 1024);
-          umma_f16(tm_s0 + buf * N1, ad, bd, idesc1, k != 0);
-        }
-        umma_commit(&sfull[buf]);
-      };
-      mma1(0);
-      for (int i = 0; i < ntiles; ++i) {
-        if (i + 1 < ntiles) mma1(i + 1);
-        const int stage = i % kStages, wb = i % NBUF;
-        mbar_wait_idle(&wfull[wb], (i / NBUF) & 1);
-        tc_fence_after();
-        const uint32_t sh = smem_u32(tiles + (size_t)stage * kTile);
-        const uint32_t swb = sw + wb * kWBox;
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-          for (int k = 0; k < kTM / 16; ++k) {
-            // h^T: two 64-feature boxes (16 KB apart) per 128-feature half, 16 patch rows = 2048 B per k-step
-            const uint64_t ad = umma_desc_sw128(sh + hf * 2 * kBox + k * 2048, kBox, 1024);
-            const uint64_t bd = umma_desc_sw128(swb + k * 2048, kWBox, 1024);
-            umma_f16(tm_acc + hf * 64, ad, bd, idesc2, (i | k) != 0);
+          for (int k = 0; k < kD / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(sh + (k >> 2) * kBox + (k & 3) * 32, 0, 1024);
+            const uint64_t bd = umma_desc_sw128(sg + (k >> 2) * (N1 * 128) + (k & 3) * 32, 0, 1024);
+            umma_f16(tm_s0 + buf * N1, ad, bd, idesc1, k != 0);
           }
+          umma_commit(&sfull[buf]);
+          continue;
         }
-        if (MODE == MODE_FWD) {
+        if (next2 < next1 && mbar_test(&wfull[next2 % NBUF], (next2 / NBUF) & 1)) {
+          const int i = next2++, stage = i % kStages, wb = i % NBUF;
+          tc_fence_after();
+          const uint32_t sh = smem_u32(tiles + (size_t)stage * kTile);
+          const uint32_t swb = sw + wb * kWBox;
 #pragma unroll
-          for (int k = 0; k < kTM / 16; ++k) {
-            const uint64_t ad = umma_desc_sw128(so + (k & 3) * 32, 0, 1024);
-            const uint64_t bd = umma_desc_sw128(swb + k * 2048, kWBox, 1024);
-            umma_f16(tm_l, ad, bd, idescl, (i | k) != 0);
+          for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+            for (int k = 0; k < kTM / 16; ++k) {
+              // h^T: two 64-feature boxes (16 KB apart) per 128-feature half, 16 patch rows = 2048 B per k-step
+              const uint64_t ad = umma_desc_sw128(sh + hf * 2 * kBox + k * 2048, kBox, 1024);
+              const uint64_t bd = umma_desc_sw128(swb + k * 2048, kWBox, 1024);
+              umma_f16(tm_acc + hf * 64, ad, bd, idesc2, (i | k) != 0);
+            }
           }
+          umma_commit(&empty[stage]);
+          umma_commit(&wempty[wb]);
+          umma_commit(accdone);
+          if (i == ntiles - 1) umma_commit(alldone);
+          continue;
         }
-        umma_commit(&empty[stage]);
-        umma_commit(&wempty[wb]);
-        umma_commit(accdone);
-        if (i == ntiles - 1) umma_commit(alldone);
+        __nanosleep(32);
       }
     }
   } else {
@@ -246,6 +240,9 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
     const int n = warp * 32 + lane;                       // row inside the tile = TMEM lane
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     uint8_t* wrow_base = s_w + n * 128;
+    float lpart[PP / 32];                                 // fwd: lane l holds this warp's sum of column l (+32)
+#pragma unroll
+    for (int c = 0; c < PP / 32; ++c) lpart[c] = 0.f;
     for (int i = 0; i < ntiles; ++i) {
       const int buf = i & 1, wb = i % NBUF;
       const bool row_ok = row_begin + (t0 + i) * kTM + n < row_end;
@@ -284,6 +281,8 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
             s_m[n] = m_new;
           }
           bar_sync(2, 128);
+#pragma unroll
+          for (int c = 0; c < PP / 32; ++c) lpart[c] *= s_alpha[c * 32 + lane];
           if (i > 0) {
             // MMA2 of tile i-1 retired.  S of tile i exists, so MMA1(i) and everything issued before it, MMA2(i-2)
             // included, has completed (the tensor pipe retires in issue order): accdone has seen i-1 or i commits and
@@ -291,7 +290,7 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
             mbar_wait(accdone, (i - 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int r = 0; r < 3; ++r) {                               // acc half 0, acc half 1, l
+            for (int r = 0; r < 2; ++r) {                               // acc half 0, acc half 1
 #pragma unroll 1
               for (int c0 = 0; c0 < PP; c0 += 32) {
                 uint32_t v[32];
@@ -326,15 +325,35 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&sempty[buf]);
       }
+      uint32_t pk[PP / 2];
+#pragma unroll
+      for (int e = 0; e < PP / 2; ++e) pk[e] = pack_bf16x2(w[2 * e], w[2 * e + 1]);
+      if (MODE == MODE_FWD) {
+        // normaliser from the ROUNDED weights: transposing butterfly, 31 shuffles per 32 columns, lane l ends with column l
+#pragma unroll
+        for (int c = 0; c < PP / 32; ++c) {
+          float v[32];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { v[2 * e] = bf16lo(pk[c * 16 + e]); v[2 * e + 1] = bf16hi(pk[c * 16 + e]); }
+#pragma unroll
+          for (int sft = 16; sft >= 1; sft >>= 1) {
+            const bool up = (lane & sft) != 0;
+#pragma unroll
+            for (int j = 0; j < sft; ++j) {
+              const float send = up ? v[j] : v[j + sft];
+              const float keep = up ? v[j + sft] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+            }
+          }
+          lpart[c] += v[0];
+        }
+      }
       // ---- w -> shared memory (MN-major B operand of MMA2), once the MMA2 that last read this buffer retired ----
       mbar_wait(&wempty[wb], ((i / NBUF) & 1) ^ 1);
       uint8_t* wrow = wrow_base + wb * kWBox;
 #pragma unroll
-      for (int c = 0; c < PP / 8; ++c) {
-        const uint4 pk = make_uint4(pack_bf16x2(w[8 * c], w[8 * c + 1]), pack_bf16x2(w[8 * c + 2], w[8 * c + 3]),
-                                    pack_bf16x2(w[8 * c + 4], w[8 * c + 5]), pack_bf16x2(w[8 * c + 6], w[8 * c + 7]));
-        *reinterpret_cast<uint4*>(wrow + ((c ^ (n & 7)) << 4)) = pk;
-      }
+      for (int c = 0; c < PP / 8; ++c)
+        *reinterpret_cast<uint4*>(wrow + ((c ^ (n & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&wfull[wb]);
@@ -354,20 +373,15 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
         for (int e = 0; e < 32; ++e) out_acc[(size_t)(c0 + e) * kD + hf * 128 + n] = __uint_as_float(v[e]);
       }
     }
-    if (MODE == MODE_FWD && warp == 0) {
+    if (MODE == MODE_FWD) {
       float* out_ml = p.part_ml + ((size_t)b * p.nsplit + split) * 2 * PP;
-#pragma unroll 1
-      for (int c0 = 0; c0 < PP; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tm_l + lane_addr + c0, v);                           // every lane of l holds the same row
-        tmem_ld_wait();
-        if (lane == 0) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) out_ml[PP + c0 + e] = __uint_as_float(v[e]);
-        }
+      for (int c = 0; c < PP / 32; ++c) s_wmax[warp * 64 + c * 32 + lane] = lpart[c];
+      bar_sync(2, 128);
+      if (n < PP) {
+        out_ml[n] = s_m[n] * kLn2;
+        out_ml[PP + n] = s_wmax[n] + s_wmax[64 + n] + s_wmax[128 + n] + s_wmax[192 + n];
       }
-      if (lane == 0)
-        for (int e = 0; e < PP; ++e) out_ml[e] = s_m[e] * kLn2;
     }
   }
   tc_fence_before();
