@@ -528,29 +528,48 @@ pool_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const DzParams p) {
     mbar_fence_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, 512);
-  // G = [q~_0 ; dpooled_0 ; q~_1 ; dpooled_1] as bf16 boxes (padded prototypes are zero rows)
-  for (int i = threadIdx.x; i < NCOL * 64; i += kZThreads) {
-    const int r = i >> 6, c = (i & 63) << 2;
-    const int blk = r / (2 * PP), within = r % (2 * PP), pi = within % PP;
-    const bool is_dp = within >= PP;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pi < p.P) {
-      const float* src = is_dp ? p.dpool[blk] + (size_t)b * p.dpool_stride[blk] : p.qt[blk] + (size_t)b * p.qt_stride[blk];
-      v = *reinterpret_cast<const float4*>(src + (size_t)pi * kD + c);
-    }
-    const uint32_t off = (uint32_t)((c >> 6) * (NCOL * 128) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
-    *reinterpret_cast<uint2*>(s_g + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-  }
-  for (int i = threadIdx.x; i < NB * PP; i += kZThreads) {
-    const int blk = i / PP, pi = i % PP;
-    s_lse[i] = pi < p.P ? p.lse[blk][(size_t)b * p.P + pi] : INFINITY;      // padded prototypes: a = 0
-    s_delta[i] = pi < p.P ? p.delta[blk][(size_t)b * p.P + pi] : 0.f;
-  }
-  fence_proxy_async_smem();                      // G was written by the generic proxy, the MMAs read it through the async proxy
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();                               // barriers initialised, TMEM allocated: the TMA warp starts streaming h now
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp != 8) {
+    // G = [q~_0 ; dpooled_0 ; q~_1 ; dpooled_1] as bf16 boxes (padded prototypes are zero rows), staged by the other
+    // nine warps with the loads issued four deep (a load -> pack -> store chain per item was 10 % of the kernel)
+    const int tid = warp == 9 ? 256 + lane : threadIdx.x;       // 288 workers
+    constexpr int kWorkers = 288, kItems = NCOL * 64;
+    for (int base = tid; base < kItems; base += 4 * kWorkers) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * kWorkers;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < kItems) {
+          const int r = i >> 6, c = (i & 63) << 2;
+          const int blk = r / (2 * PP), within = r % (2 * PP), pi = within % PP;
+          if (pi < p.P) {
+            const float* src = within >= PP ? p.dpool[blk] + (size_t)b * p.dpool_stride[blk] : p.qt[blk] + (size_t)b * p.qt_stride[blk];
+            v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)pi * kD + c));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * kWorkers;
+        if (i < kItems) {
+          const int r = i >> 6, c = (i & 63) << 2;
+          const uint32_t off = (uint32_t)((c >> 6) * (NCOL * 128) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
+          *reinterpret_cast<uint2*>(s_g + off) = make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
+        }
+      }
+    }
+    for (int i = tid; i < NB * PP; i += kWorkers) {
+      const int blk = i / PP, pi = i % PP;
+      s_lse[i] = pi < p.P ? p.lse[blk][(size_t)b * p.P + pi] : INFINITY;      // padded prototypes: a = 0
+      s_delta[i] = pi < p.P ? p.delta[blk][(size_t)b * p.P + pi] : 0.f;
+    }
+    fence_proxy_async_smem();                    // G was written by the generic proxy, the MMAs read it through the async proxy
+    bar_sync(3, kWorkers);
+  }
   const uint32_t tm_s = tmem_base, tm_d = tmem_base + 128, tm_q = tmem_base + 384;   // S | dh | dq~^T (2 x 64 columns)
   // dq~ of block p.dq_block rides along: dq~^T[f][p] += sum_n h[n][f] dS[n][p] with A = h^T (the tile read MN-major) and
   // B = the 64-column box of E that holds dS of that block (the same image MMA2 reads K-major, here MN-major)

@@ -144,35 +144,54 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
     mbar_fence_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, 512);
-  // G as bf16 boxes (padded prototypes are zero rows)
-  for (int i = threadIdx.x; i < N1 * 64; i += kThreads) {
-    const int r = i >> 6, c = (i & 63) << 2;
-    const int pi = r % PP;
-    const bool is_dp = r >= PP;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pi < p.P) {
-      const float* src = is_dp ? p.dpool + (size_t)b * p.dpool_stride : p.qt + (size_t)b * p.qt_stride;
-      v = *reinterpret_cast<const float4*>(src + (size_t)pi * kD + c);
-    }
-    const uint32_t off = (uint32_t)((c >> 6) * (N1 * 128) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
-    *reinterpret_cast<uint2*>(s_g + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-  }
-  for (int i = threadIdx.x; i < NBUF * kWBox / 16; i += kThreads) reinterpret_cast<uint4*>(s_w)[i] = make_uint4(0u, 0u, 0u, 0u);
-  if (MODE == MODE_FWD) {
-    for (int i = threadIdx.x; i < 64; i += kThreads) { s_m[i] = -INFINITY; s_alpha[i] = 0.f; }
-  } else {
-    for (int i = threadIdx.x; i < 64; i += kThreads) {
-      const bool ok = i < p.P;
-      s_m[i] = ok ? p.lse[(size_t)b * p.P + i] * kLog2e : INFINITY;       // padded prototypes: a = 0
-      s_alpha[i] = ok ? p.delta[(size_t)b * p.P + i] : 0.f;
-    }
-  }
-  fence_proxy_async_smem();                      // G / ones / zeroed w: generic-proxy writes read by the MMAs
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();                               // barriers initialised, TMEM allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_s0 = tmem_base, tm_acc = tmem_base + 256;   // S: 2 x N1 <= 256 columns; acc: 2 x 64
+  if (warp != 4) {
+    // The h tiles are already on their way (the TMA warp below does not wait for this): stage G and the small tables
+    // with the other five warps.  Loads are issued four deep -- a load -> pack -> store chain per item made this
+    // prologue 10 % of the kernel (one L2 round trip per iteration).
+    const int tid = warp == 5 ? 128 + lane : threadIdx.x;       // 160 workers
+    constexpr int kWorkers = 160, kItems = N1 * 64;
+    for (int base = tid; base < kItems; base += 4 * kWorkers) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * kWorkers;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < kItems) {
+          const int r = i >> 6, c = (i & 63) << 2, pi = r % PP;
+          if (pi < p.P) {
+            const float* src = r >= PP ? p.dpool + (size_t)b * p.dpool_stride : p.qt + (size_t)b * p.qt_stride;
+            v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)pi * kD + c));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * kWorkers;
+        if (i < kItems) {
+          const int r = i >> 6, c = (i & 63) << 2;
+          const uint32_t off = (uint32_t)((c >> 6) * (N1 * 128) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
+          *reinterpret_cast<uint2*>(s_g + off) = make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
+        }
+      }
+    }
+    for (int i = tid; i < NBUF * kWBox / 16; i += kWorkers) reinterpret_cast<uint4*>(s_w)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (MODE == MODE_FWD) {
+      for (int i = tid; i < 64; i += kWorkers) { s_m[i] = -INFINITY; s_alpha[i] = 0.f; }
+    } else {
+      for (int i = tid; i < 64; i += kWorkers) {
+        const bool ok = i < p.P;
+        s_m[i] = ok ? p.lse[(size_t)b * p.P + i] * kLog2e : INFINITY;       // padded prototypes: a = 0
+        s_alpha[i] = ok ? p.delta[(size_t)b * p.P + i] : 0.f;
+      }
+    }
+    fence_proxy_async_smem();                    // G / zeroed w: generic-proxy writes read by the MMAs
+    bar_sync(3, kWorkers);
+  }
 
   if (warp == 4) {
     // ------------------------------ TMA producer ------------------------------
