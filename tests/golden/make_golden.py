@@ -136,6 +136,82 @@ def gen_model(seed):
     npz("model_P6_eval.npz", **arrs)
 
 
+def gen_model_full(seed):
+    """The WHOLE UMEML_GAN (P = 6) with every parameter set by util_hotpath.fill_state(seed): eval forward with masks,
+    train forward (7-tuple) + the gradients of NLL + KD + modularity, the cca tuple, and one GAN phase (in-forward
+    optimiser steps).  Nystrom output dropout (hard-coded 0.1, ops/blocks.py:262) is switched off on the module for
+    the train-mode runs so that they are deterministic."""
+    import json
+    from util_hotpath import fill_state
+    model = R.build_reference_model(seed=seed, dropout=0.0)
+    fill_state(model, seed)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    torch.manual_seed(seed + 1)
+    lens, npad, G = [96, 57, 120], 128, sum(R.GROUP_SIZES)
+    img = torch.full((len(lens), npad, 512), -10000.0)
+    for i, n in enumerate(lens):
+        img[i, :n] = torch.randn(n, 512)
+    omic = torch.rand(len(lens), G)
+    model.omic_means = torch.rand(G)
+    without = torch.tensor([0, 1, 0])
+    insample = (torch.rand(len(lens), G) < 0.3).int()
+    label, cens = torch.tensor([1, 3, 0]), torch.tensor([0, 1, 0])
+    arrs = {"img": img, "omic": omic, "omic_means": model.omic_means, "without_omic": without, "insample_without_omic": insample,
+            "label": label, "censorship": cens, "p_proto_init": model.p_proto.clone(), "param_seed": seed, "lens": np.array(lens)}
+    for k, ix in enumerate(model.gene_group_indexes):
+        arrs["group_%d" % k] = np.array(ix)
+    arrs["state_keys"] = np.array(json.dumps({k: list(v.shape) for k, v in model.state_dict().items()}))
+    cap = {}
+    hooks = [model.proto_g_blocks[1].register_forward_hook(lambda m, i, o: cap.setdefault("p", []).append(o.detach().clone())),
+             model.layer_norm_p.register_forward_hook(lambda m, i, o: cap.__setitem__("h_path", o.detach().clone())),
+             model.layer_norm_o.register_forward_hook(lambda m, i, o: cap.__setitem__("h_omic", o.detach().clone()))]
+    for k, net in enumerate(model.omic_net):
+        hooks.append(net.register_forward_hook(lambda m, i, o, k=k: cap.__setitem__("omic_%d" % k, o.detach().clone())))
+    # (1) eval with both kinds of masks
+    with torch.no_grad():
+        logits = R.run_reference_forward(model, {"img": img, "omic": omic, "patient_id": ["a", "b", "c"], "without_omic": without,
+                                                 "insample_without_omic": insample}, train=False)
+    arrs.update({"eval.logits": logits, "eval.p_proto": torch.cat(cap["p"][-len(lens):], 0), "eval.h_path": cap["h_path"],
+                 "eval.h_omic": cap["h_omic"], "eval.h_omic_bag": torch.cat([cap["omic_%d" % k] for k in range(6)], dim=1)})
+    # (2) eval without omics at all (generator output replaces the omic tokens, umeml_gan.py:506-507)
+    with torch.no_grad():
+        arrs["eval_noomic.logits"] = R.run_reference_forward(model, {"img": img, "omic": None, "patient_id": ["a", "b", "c"],
+                                                                     "insample_without_omic": torch.zeros(len(lens), G)}, train=False)
+    # (3) train step: loss = NLL + KD + modularity (mbtrain.py:182-186), gradients
+    cap.clear()
+    model.zero_grad()
+    out = R.run_reference_forward(model, {"img": img, "omic": omic, "patient_id": ["a", "b", "c"]}, train=True)
+    loss_mod = R.load_model_module()
+    import importlib
+    nll = importlib.import_module("medmm.loss.loss").nll_loss_new
+    loss = nll(logits=out, Y=label, c=cens) + out[-2] + out[1]
+    loss.backward()
+    arrs.update({"train.logits": out[0], "train.modular_loss": out[1], "train.loss_kd": out[5], "train.importance_path": out[6],
+                 "train.loss": loss, "train.p_proto": torch.cat(cap["p"][-len(lens):], 0), "train.h_omic": cap["h_omic"]})
+    for k in ("classifier.weight", "path_net.0.weight", "bottleattn.linear_p.weight", "omic_encoder.0.attn.attn.to_qkv.weight",
+              "proto_g_blocks.1.cross_attn.in_proj_weight", "omic_net.4.0.weight", "explainer_path.weight", "p_encoder_token"):
+        arrs["train.grad." + k] = dict(model.named_parameters())[k].grad.clone()
+    # (4) cca tuple
+    model.cca = True
+    with torch.no_grad():
+        cca = R.run_reference_forward(model, {"img": img, "omic": omic, "patient_id": ["a", "b", "c"]}, train=False)
+    model.cca = False
+    arrs.update({"cca.h_path": cca[0], "cca.h_omic": cca[1], "cca.p_proto_before": cca[2], "cca.h_omic_bag_before": cca[3]})
+    # (5) GAN phase + replace_ratio swap: three in-forward optimiser steps, numpy RNG for the swap
+    model.train_gan, model.replace_ratio = True, 0.5
+    np.random.seed(1234)
+    out = R.run_reference_forward(model, {"img": img, "omic": omic, "patient_id": ["a", "b", "c"]}, train=True)
+    model.train_gan, model.replace_ratio = False, 0
+    arrs.update({"gan.gen_loss": out[2], "gan.dis_p_loss": out[3], "gan.dis_o_loss": out[4], "gan.logits": out[0],
+                 "gan.p2o_w0_after": model.gan_generator_p2o.net[0].weight.detach()[:8, :64].clone(),
+                 "gan.dis_o_w0_after": model.gan_discriminator_o.layers[0].weight.detach()[:8, :64].clone()})
+    for h in hooks:
+        h.remove()
+    npz("model_P6_full.npz", **arrs)
+
+
 def gen_distance(seed):
     """euclidean_squared_distance (metrics/distance.py:46-61): the only reference arithmetic behind A9."""
     dist = R.load_distance()
@@ -154,4 +230,5 @@ if __name__ == "__main__":
     gen_modularity(ops, 7, 257, 4)
     gen_chain(mod, ops, 16, 384, 5)
     gen_model(6)
+    gen_model_full(8)
     gen_distance(7)

@@ -1,0 +1,117 @@
+"""The drop-in ``umeml_gan`` model end to end on the GPU against the EXECUTED reference (tests/golden/model_P6_full.npz):
+``build_model("umeml_gan", cfg=..., num_classes=4, omic_sizes=1000)`` -> ``model(batch)`` with the reference batch dict
+(img (B,Npad,512) fp32 with -10000 padding, omic, masks) -> logits in eval, the 7-tuple in train, the training loss
+and its gradients.  Hot path on the sm_100a kernels, token tail in batched torch."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from test_model_tail_cpu import build, load, make_cfg
+from util_hotpath import Ledger, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(z, dev, **extra):
+    b = {"img": z["img"].to(dev), "omic": z["omic"].to(dev), "patient_id": ["a", "b", "c"]}
+    for k, v in extra.items():
+        b[k] = v.to(dev) if isinstance(v, torch.Tensor) else v
+    return b
+
+
+def test_eval_logits_match_reference(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    z = load()
+    dev = "cuda"
+    model = build(z).to(dev).eval()
+    L = Ledger("drop-in umeml_gan, eval (P=6)")
+    with torch.no_grad():
+        logits = model(_batch(z, dev, without_omic=z["without_omic"], insample_without_omic=z["insample_without_omic"]))
+        L.add("logits (with missing-omics masks)", rel(logits, z["eval.logits"]), 1e-3, "executed reference")
+        from imp_b200 import survival
+        from oracle import imp_oracle as O
+        L.add("risk scores", rel(survival.risk(logits), O.survival_risk(z["eval.logits"])), 1e-3, "executed reference")
+        b = _batch(z, dev)
+        b["omic"] = None
+        L.add("logits (no omics: generator tokens)", rel(model(b), z["eval_noomic.logits"]), 1e-3, "executed reference")
+    L.assert_ok()
+
+
+def test_train_tuple_loss_and_gradients_match_reference(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    from imp_b200 import survival
+    z = load()
+    dev = "cuda"
+    model = build(z).to(dev).train()
+    out = model(_batch(z, dev))
+    assert isinstance(out, tuple) and len(out) == 7
+    L = Ledger("drop-in umeml_gan, train (P=6)")
+    L.add("logits", rel(out[0], z["train.logits"]), 1e-3, "executed reference")
+    ref_mod = z["train.modular_loss"].item()
+    L.add("modular_loss", max(0.0, abs(out[1].item() - ref_mod) - 1e-4) / abs(ref_mod), 1e-3, "executed reference",
+          "two groups, mean over 3 bags of ~100 patches; 1e-4 absolute for the trace cancellation")
+    L.add("loss_kd", abs(out[5].item() - z["train.loss_kd"].item()) / abs(z["train.loss_kd"].item()), 2e-3, "executed reference")
+    L.add("importance_path", rel(out[6], z["train.importance_path"]), 1e-3, "executed reference")
+    loss = survival.nll_loss_new(out, z["label"].to(dev), z["censorship"].to(dev)) + out[5] + out[1]
+    L.add("training loss (NLL + KD + modularity)", abs(loss.item() - z["train.loss"].item()) / abs(z["train.loss"].item()), 1e-3,
+          "executed reference")
+    loss.backward()
+    named = dict(model.named_parameters())
+    for k in ("classifier.weight", "bottleattn.linear_p.weight", "omic_encoder.0.attn.attn.to_qkv.weight", "explainer_path.weight",
+              "p_encoder_token", "omic_net.4.0.weight", "proto_g_blocks.1.cross_attn.in_proj_weight", "path_net.0.weight"):
+        # ~100-patch bags: the modularity gradient is in its small-graph regime (tests/test_modularity_gpu.py, 1e-2)
+        L.add("grad " + k, rel(named[k].grad, z["train.grad." + k]), 2e-2, "executed reference",
+              "fp32 fixture rounded to bf16; small-graph modularity gradient")
+    L.assert_ok()
+
+
+def test_cca_and_gan_modes(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    z = load()
+    dev = "cuda"
+    model = build(z).to(dev).eval()
+    model.cca = True
+    with torch.no_grad():
+        out = model(_batch(z, dev))
+    assert len(out) == 5 and out[4] == "cca"
+    L = Ledger("drop-in umeml_gan, cca / gan (P=6)")
+    L.add("cca h_path", rel(out[0], z["cca.h_path"]), 1e-3, "executed reference")
+    L.add("cca h_omic", rel(out[1], z["cca.h_omic"]), 1e-3, "executed reference")
+    L.add("cca p_proto_before", rel(out[2], z["cca.p_proto_before"]), 1e-3, "executed reference")
+    model.cca = False
+    model.train()
+    model.train_gan, model.replace_ratio = True, 0.5
+    np.random.seed(1234)
+    out = model(_batch(z, dev))
+    for name, idx in (("gan.gen_loss", 2), ("gan.dis_p_loss", 3), ("gan.dis_o_loss", 4)):
+        L.add(name, abs(float(out[idx]) - z[name].item()) / abs(z[name].item()), 1e-3, "executed reference")
+    L.add("generator weights after the in-forward Adam step", rel(model.gan_generator_p2o.net[0].weight.detach()[:8, :64], z["gan.p2o_w0_after"]),
+          1e-4, "executed reference")
+    L.assert_ok()
+
+
+def test_p32_model_runs_a_training_step(tmp_path, monkeypatch):
+    """MODEL.UMEML.PROTOTYPES = 32 (BASELINE configs[1]; the reference cannot be built at P != 6) with dropout
+    0.25 and bf16 token tail (TRAINER.PREC = 'bf16'): finite loss and gradients for every trainable tensor that the
+    loss reaches, packed wire format in."""
+    monkeypatch.chdir(tmp_path)
+    from imp_b200 import survival, wire
+    from imp_b200.registry import build_model
+    dev = "cuda"
+    torch.manual_seed(0)
+    for prec in ("fp32", "bf16"):
+        model = build_model("umeml_gan", verbose=False, cfg=make_cfg(n_proto=32, dropout=0.25, prec=prec), num_classes=4, omic_sizes=1000).to(dev).train()
+        bags = [torch.randn(n, 512) for n in (700, 1300)]
+        batch = wire.to_device(wire.pack_bags(bags, pin=False), dev)
+        batch["omic"] = torch.rand(2, 3354, device=dev)
+        batch["patient_id"] = ["x", "y"]
+        out = model(batch)
+        assert out[0].shape == (2, 4) and out[6].shape == (2, 32)
+        loss = survival.nll_loss_new(out, torch.tensor([1, 2], device=dev), torch.tensor([0, 1], device=dev)) + out[5] + out[1]
+        loss.backward()
+        assert torch.isfinite(loss).item()
+        missing = [k for k, p in model.named_parameters() if p.grad is None and not k.startswith(("gan_", "g_omic_net"))]
+        assert not missing, missing
+        assert all(torch.isfinite(p.grad).all().item() for p in model.parameters() if p.grad is not None)

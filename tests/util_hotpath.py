@@ -99,3 +99,29 @@ class Ledger:
 
     def assert_ok(self):
         assert not self.bad, "%s: %s" % (self.test, "; ".join(self.bad))
+
+
+def fill_state(module, seed: int):
+    """Deterministic parameters for EVERY entry of ``module.state_dict()`` from (seed, key name): used both on the
+    executed reference (tests/golden/make_golden.py) and on this repo's drop-in model, so that a fixture only has to
+    store the seed.  Weights U(-1/sqrt(fan_in), 1/sqrt(fan_in)), biases 0.02 N(0,1), LayerNorm gains 1 + 0.1 N(0,1),
+    learned tokens U(0,1)."""
+    import zlib
+    sd = module.state_dict()
+    out = {}
+    for k in sorted(sd):
+        t = sd[k]
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(k.encode())) % (2 ** 31))
+        if not t.dtype.is_floating_point:
+            out[k] = t.clone()
+        elif k.endswith("_token") or k.endswith("bottle_tokens"):
+            out[k] = torch.rand(t.shape, generator=g)
+        elif t.dim() >= 2:
+            fan_in = int(torch.tensor(t.shape[1:]).prod())
+            out[k] = (torch.rand(t.shape, generator=g) * 2 - 1) / math.sqrt(max(fan_in, 1))
+        elif "norm" in k and k.endswith("weight"):
+            out[k] = 1.0 + 0.1 * torch.randn(t.shape, generator=g)
+        else:
+            out[k] = 0.02 * torch.randn(t.shape, generator=g)
+    module.load_state_dict(out, strict=True)
+    return out
