@@ -59,29 +59,29 @@ def test_product_package_does_not_import_the_oracle():
             assert "oracle" not in src.replace("imp_oracle.py", ""), fn
 
 
-@pytest.mark.parametrize("n_proto", [16, 32])
+@pytest.mark.parametrize("n_proto", [16, 32, 64])
 @pytest.mark.parametrize("max_len", [4096, 16384, 120000])
 def test_pool_split_plan_fills_whole_waves(max_len, n_proto):
-    """The pooling kernels split every bag into runs of 64-row tiles; the number of runs is visible through the
-    workspace query (B * nsplit partial states of P x 258 floats).  On the 148-SM default (no GPU here) with two
-    CTAs per SM the B * nsplit CTAs must not leave a nearly empty last wave (the first version launched 608 CTAs on
-    296 slots for 32 bags: 2.05 waves), and a CTA keeps at least 8 tiles unless the bag is shorter."""
+    """The pooling kernels (pool_tc.cu) split every bag into runs of 128-row tiles; the number of runs is visible
+    through the workspace query (B * nsplit partial states of PP x 258 floats, PP = 32 or 64).  On the 148-SM default
+    (no GPU here) with one CTA per SM the B * nsplit CTAs must not leave a nearly empty last wave (the first version
+    launched 608 CTAs on 296 slots for 32 bags: 2.05 waves), and a CTA keeps at least 4 tiles unless the bag is shorter."""
     from imp_b200 import _lib
     lib = _lib.lib()
     lib.imp_pool_fwd_workspace_bytes.restype = ctypes.c_size_t
-    slots = 2 * 148
-    tiles = (max_len + 63) // 64
-    pp = 16 if n_proto <= 16 else 32
+    slots = 148
+    tiles = (max_len + 127) // 128
+    pp = 32 if n_proto <= 32 else 64
     for bags in (1, 2, 3, 8, 16, 32, 64, 200):
         nbytes = lib.imp_pool_fwd_workspace_bytes(bags, max_len, n_proto)
         nsplit, rem = divmod(nbytes, 4 * bags * pp * 258)
-        assert rem == 0 and 1 <= nsplit <= max(1, tiles // 8), (bags, nsplit)
+        assert rem == 0 and 1 <= nsplit <= max(1, tiles // 4), (bags, nsplit)
         ctas = bags * nsplit
         waves = -(-ctas // slots)
         tiles_per_cta = -(-tiles // nsplit)
         # no plan with fewer wave-steps exists among the admissible split counts
         best = min((-(-bags * (-(-tiles // (-(-tiles // ns))) ) // slots)) * (-(-tiles // ns) + 1)
-                   for ns in range(1, max(1, min(tiles // 8, 256)) + 1))
+                   for ns in range(1, max(1, min(tiles // 4, 128)) + 1))
         assert waves * (tiles_per_cta + 1) == best, (bags, nsplit, waves, tiles_per_cta, best)
         if ctas > slots:
             assert ctas / (waves * slots) > 0.6, (bags, nsplit, ctas)
