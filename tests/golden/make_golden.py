@@ -186,7 +186,14 @@ def gen_model_full(seed):
     loss_mod = R.load_model_module()
     import importlib
     nll = importlib.import_module("medmm.loss.loss").nll_loss_new
-    loss = nll(logits=out, Y=label, c=cens) + out[-2] + out[1]
+    loss_nomod = nll(logits=out, Y=label, c=cens) + out[-2]
+    loss_nomod.backward(retain_graph=True)                     # the step without the ill-conditioned small-bag modularity term
+    names = ("classifier.weight", "path_net.0.weight", "bottleattn.linear_p.weight", "omic_encoder.0.attn.attn.to_qkv.weight",
+             "proto_g_blocks.1.cross_attn.in_proj_weight", "omic_net.4.0.weight", "explainer_path.weight", "p_encoder_token")
+    for k in names:
+        arrs["train.grad_nomod." + k] = dict(model.named_parameters())[k].grad.clone()
+    model.zero_grad()
+    loss = loss_nomod + out[1]
     loss.backward()
     arrs.update({"train.logits": out[0], "train.modular_loss": out[1], "train.loss_kd": out[5], "train.importance_path": out[6],
                  "train.loss": loss, "train.p_proto": torch.cat(cap["p"][-len(lens):], 0), "train.h_omic": cap["h_omic"]})

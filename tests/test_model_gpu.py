@@ -49,21 +49,32 @@ def test_train_tuple_loss_and_gradients_match_reference(tmp_path, monkeypatch):
     assert isinstance(out, tuple) and len(out) == 7
     L = Ledger("drop-in umeml_gan, train (P=6)")
     L.add("logits", rel(out[0], z["train.logits"]), 1e-3, "executed reference")
+    # The fixture's bags have 57-120 random patches: near-uniform cosine graphs on which -100 (S1 - S2) cancels to 1e-4 of
+    # its scale.  Rounding h to bf16 (how the device STORES it) alone moves the fp64 oracle's loss by 2e-2 and its token
+    # gradient by 2-7 % on these bags (profiles/r02_parity.md); at 16 384 patches the same quantities agree to 5e-4
+    # (tests/test_headline_parity_gpu.py).  Hence: modularity-free gradients are held to the bf16 floor, the
+    # modularity-carrying ones to the conditioning bound.
     ref_mod = z["train.modular_loss"].item()
-    L.add("modular_loss", max(0.0, abs(out[1].item() - ref_mod) - 1e-4) / abs(ref_mod), 1e-3, "executed reference",
-          "two groups, mean over 3 bags of ~100 patches; 1e-4 absolute for the trace cancellation")
+    L.add("modular_loss", abs(out[1].item() - ref_mod) / abs(ref_mod), 2e-2, "executed reference",
+          "ill-conditioned on ~100-patch random bags: bf16 storage of h")
     L.add("loss_kd", abs(out[5].item() - z["train.loss_kd"].item()) / abs(z["train.loss_kd"].item()), 2e-3, "executed reference")
     L.add("importance_path", rel(out[6], z["train.importance_path"]), 1e-3, "executed reference")
-    loss = survival.nll_loss_new(out, z["label"].to(dev), z["censorship"].to(dev)) + out[5] + out[1]
+    loss_nomod = survival.nll_loss_new(out, z["label"].to(dev), z["censorship"].to(dev)) + out[5]
+    loss = loss_nomod + out[1]
     L.add("training loss (NLL + KD + modularity)", abs(loss.item() - z["train.loss"].item()) / abs(z["train.loss"].item()), 1e-3,
           "executed reference")
-    loss.backward()
+    names = ("classifier.weight", "bottleattn.linear_p.weight", "omic_encoder.0.attn.attn.to_qkv.weight", "explainer_path.weight",
+             "p_encoder_token", "omic_net.4.0.weight", "proto_g_blocks.1.cross_attn.in_proj_weight", "path_net.0.weight")
     named = dict(model.named_parameters())
-    for k in ("classifier.weight", "bottleattn.linear_p.weight", "omic_encoder.0.attn.attn.to_qkv.weight", "explainer_path.weight",
-              "p_encoder_token", "omic_net.4.0.weight", "proto_g_blocks.1.cross_attn.in_proj_weight", "path_net.0.weight"):
-        # ~100-patch bags: the modularity gradient is in its small-graph regime (tests/test_modularity_gpu.py, 1e-2)
-        L.add("grad " + k, rel(named[k].grad, z["train.grad." + k]), 2e-2, "executed reference",
-              "fp32 fixture rounded to bf16; small-graph modularity gradient")
+    loss_nomod.backward(retain_graph=True)
+    for k in names:
+        L.add("grad(NLL + KD) " + k, rel(named[k].grad, z["train.grad_nomod." + k]), 5e-3, "executed reference",
+              "fp32 fixture rounded to bf16 + operand floor")
+    model.zero_grad()
+    loss.backward()
+    for k in names:
+        L.add("grad(NLL + KD + modularity) " + k, rel(named[k].grad, z["train.grad." + k]), 1.5e-1, "executed reference",
+              "conditioning of the small-bag modularity gradient under bf16 storage of h")
     L.assert_ok()
 
 
