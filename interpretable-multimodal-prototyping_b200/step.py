@@ -49,7 +49,7 @@ class GraphedStep:
     every dropout kernel XORs into its seed (``imp_set_seed_offset``) -- each replay draws a new mask.
     Gradients land in ``param.grad`` of the wrapped module (tensors owned by the graph's memory pool)."""
 
-    def __init__(self, runner: HotPathStep):
+    def __init__(self, runner: Optional[nn.Module]):
         self.runner = runner
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.loss: Optional[torch.Tensor] = None
@@ -57,10 +57,14 @@ class GraphedStep:
 
     def capture(self, batch: Dict, cot_proto: torch.Tensor, cot_omic: Optional[torch.Tensor], lengths=None,
                 warmup: int = 3) -> "GraphedStep":
+        return self.capture_fn(lambda: self.runner(batch, cot_proto, cot_omic, lengths), [p for p in self.runner.parameters()],
+                               cot_proto.device, warmup)
+
+    def capture_fn(self, loss_fn, params, dev, warmup: int = 3) -> "GraphedStep":
+        """Capture ``loss = loss_fn(); loss.backward()`` for any fixed-shape, sync-free step (e.g. the whole drop-in
+        ``umeml_gan`` model with ``importance_log = "defer"``): same protocol as ``capture``."""
         from . import _lib
-        import ctypes
-        dev = cot_proto.device
-        params = [p for p in self.runner.parameters()]
+        params = list(params)
         self._seed_word = torch.zeros(1, dtype=torch.int32, device=dev)
         _lib.call("imp_set_seed_offset", self._seed_word)
         _lib.profile_enable(False)
@@ -69,7 +73,7 @@ class GraphedStep:
             for p in params:
                 p.grad = None
             self._seed_word.add_(0x61C88647)                      # new keep-masks on every replay
-            loss = self.runner(batch, cot_proto, cot_omic, lengths)
+            loss = loss_fn()
             loss.backward()
             return loss
 

@@ -15,7 +15,8 @@ What runs where:
 ``MODEL.DROPOUT``, ``MODEL.HIDDEN_DIM``, ``MODEL.PROJECT_DIM``, ``MODEL.FUSION``, ``MODEL.SIZE``, ``DATASET.PATH.DIM``,
 ``DATASET.OMIC.DIM``, ``DATASET.ROOT``; additive: ``TRAINER.PREC`` ("fp32" default | "amp" | "bf16": the token tail runs
 under bf16 autocast; the N-scaling kernels always feed bf16 operands to the tensor cores and keep fp32 statistics),
-``MODEL.UMEML.ASYNC_IMPORTANCE_LOG`` (default False = the reference's synchronous appends to ``<set>_path.txt``).
+``MODEL.UMEML.IMPORTANCE_LOG`` ("sync" default = the reference's appends to ``<set>_path.txt`` inside forward | "async" |
+"defer", see ``__init__``).
 
 Differences from the reference, all in directions the reference cannot run:
   * the number of path prototypes is independent of the six gene groups (P = 16 / 32 work; at P = 6 every parameter
@@ -81,7 +82,11 @@ class UMEML_GAN(IMPHotPath):
         self.size = _cfg(cfg, "MODEL.SIZE", "small")
         self.n_reg = int(_cfg(cfg, "MODEL.UMEML.REGISTERS", 3))
         self.prec = str(_cfg(cfg, "TRAINER.PREC", "fp32"))
-        self.async_importance_log = bool(_cfg(cfg, "MODEL.UMEML.ASYNC_IMPORTANCE_LOG", False))
+        # "sync": append to <set>_path.txt / <set>_omic.txt inside forward like the reference (default); "async": pinned
+        # copy now, file append once the copy has completed; "defer": keep the device tensors of the last forward in
+        # ``self.last_importance`` and write nothing (CUDA-graph capture; ``flush_importance_logs`` appends them)
+        self.importance_log = str(_cfg(cfg, "MODEL.UMEML.IMPORTANCE_LOG", "async" if _cfg(cfg, "MODEL.UMEML.ASYNC_IMPORTANCE_LOG", False) else "sync"))
+        self.last_importance: Dict[str, torch.Tensor] = {}
         n_omic_tok = len(groups) + 1                                   # o_encoder_token + one token per gene group
         n_path_tok = n_proto + 1
 
@@ -171,7 +176,10 @@ class UMEML_GAN(IMPHotPath):
         rows to pinned memory and writes them when their copy has completed (next forward / ``flush_importance_logs``)."""
         path = self.plot_set + "_" + name + ".txt"
         rows = rows.detach()
-        if self.async_importance_log and rows.is_cuda:
+        if self.importance_log == "defer":
+            self.last_importance[path] = rows
+            return
+        if self.importance_log == "async" and rows.is_cuda:
             host = torch.empty(rows.shape, dtype=rows.dtype, pin_memory=True)
             host.copy_(rows, non_blocking=True)
             ev = torch.cuda.Event()
@@ -183,6 +191,10 @@ class UMEML_GAN(IMPHotPath):
                 f.write(" ".join(map(str, row)) + "\n")
 
     def flush_importance_logs(self, wait: bool = True) -> None:
+        for path, rows in self.last_importance.items():          # "defer" mode: the rows of the last forward / graph replay
+            with open(path, "a") as f:
+                for row in rows.tolist():
+                    f.write(" ".join(map(str, row)) + "\n")
         keep = []
         for path, host, ev in self._pending_logs:
             if not wait and not ev.query():
