@@ -123,8 +123,9 @@ def test_chain_on_golden():
     L.add("tokens", rel(c, z["c_out"]), 1e-3, "executed reference")
     ref = z["modularity"].item()
     L.add("modularity", max(0.0, abs(mod.item() - ref) - 5e-5) / abs(ref), 1e-3, "executed reference")
-    # the scalar is sum(c.cot) + modularity: on 384 patches the -100 x trace term dominates the token cotangent and
-    # its gradient carries the small-graph error of the modularity kernels (1e-2 class, see above) into every tensor
+    # fp32 fixture vs bf16 device inputs: rounding x and W1 flips the ReLU mask of the few activations next to zero, each
+    # flip switches a full-size dz entry (relative Frobenius error of dW1 ~ sqrt(flipped fraction) = 3-4e-2, independent
+    # of the bag size; see tests/test_model_gpu.py); the other tensors see the small-graph modularity gradient (1e-2 class)
     for k, v in leaves.items():
         L.add("grad " + k, rel(v.grad, z["grad." + k]), 5e-2, "executed reference", "fp32 fixture rounded to bf16; modularity-dominated cotangent on 384 patches")
     # the pooling path alone on the same fixture inputs (no modularity): oracle on the bf16-rounded inputs

@@ -54,6 +54,10 @@ def test_train_tuple_loss_and_gradients_match_reference(tmp_path, monkeypatch):
     # gradient by 2-7 % on these bags (profiles/r02_parity.md); at 16 384 patches the same quantities agree to 5e-4
     # (tests/test_headline_parity_gpu.py).  Hence: modularity-free gradients are held to the bf16 floor, the
     # modularity-carrying ones to the conditioning bound.
+    # dW1 / db1 against an fp32 run on NON-bf16-representable inputs carry one more term: rounding x and W1 to bf16 moves
+    # z = x W1^T + b1 by ~4e-3 relative, which flips the ReLU mask of the ~0.1-0.2 % of activations that sit that close to
+    # zero; a flipped element switches a full-size dz entry on or off, so the relative Frobenius error is ~sqrt(fraction)
+    # = 3-4e-2 at ANY bag size (on bf16-exact inputs the same gradient agrees to 2e-3: test_headline_parity_gpu.py).
     ref_mod = z["train.modular_loss"].item()
     L.add("modular_loss", abs(out[1].item() - ref_mod) / abs(ref_mod), 2e-2, "executed reference",
           "ill-conditioned on ~100-patch random bags: bf16 storage of h")
@@ -68,8 +72,8 @@ def test_train_tuple_loss_and_gradients_match_reference(tmp_path, monkeypatch):
     named = dict(model.named_parameters())
     loss_nomod.backward(retain_graph=True)
     for k in names:
-        L.add("grad(NLL + KD) " + k, rel(named[k].grad, z["train.grad_nomod." + k]), 5e-3, "executed reference",
-              "fp32 fixture rounded to bf16 + operand floor")
+        L.add("grad(NLL + KD) " + k, rel(named[k].grad, z["train.grad_nomod." + k]), 6e-2 if k.startswith("path_net") else 5e-3,
+              "executed reference", "ReLU mask flips from rounding the fp32 fixture to bf16" if k.startswith("path_net") else "fp32 fixture rounded to bf16 + operand floor")
     model.zero_grad()
     loss.backward()
     for k in names:
