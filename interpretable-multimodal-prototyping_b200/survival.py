@@ -9,6 +9,15 @@ Both are a handful of fused elementwise ops on (B, num_bins) tensors and stay on
 from __future__ import annotations
 
 import torch
+import torch.nn.functional as F
+
+
+def _survival(x: torch.Tensor) -> torch.Tensor:
+    """prod_{j<=k} (1 - sigmoid(x_j)) = exp(-sum_{j<=k} softplus(x_j)).  Same value as the reference's
+    ``torch.cumprod(1 - hazards, dim=1)``; written as a cumulative sum because cumprod's backward probes its input for
+    zeros with a device->host sync (``(input == 0).any().item()``), which stalls the stream and cannot be captured in a
+    CUDA graph."""
+    return torch.exp(-torch.cumsum(F.softplus(x), dim=1))
 
 
 def nll_loss_new(logits, Y, c, alpha=0.0, eps=1e-7, reduction="mean"):
@@ -17,7 +26,7 @@ def nll_loss_new(logits, Y, c, alpha=0.0, eps=1e-7, reduction="mean"):
     y = Y.to(device=x.device, dtype=torch.int64).view(bsz, 1)
     cens = c.to(device=x.device, dtype=torch.int64).view(bsz, 1)
     hazards = torch.sigmoid(x)
-    surv = torch.cumprod(1 - hazards, dim=1)
+    surv = _survival(x)
     surv_pad = torch.cat([torch.ones_like(hazards[:, :1]), surv], dim=1)          # S(-1) = 1
     s_prev = surv_pad.gather(1, y).clamp(min=eps)
     h_this = hazards.gather(1, y).clamp(min=eps)
@@ -35,7 +44,7 @@ def nll_loss_new(logits, Y, c, alpha=0.0, eps=1e-7, reduction="mean"):
 
 
 def survival_curve(logits: torch.Tensor) -> torch.Tensor:
-    return torch.cumprod(1 - torch.sigmoid(logits), dim=1)
+    return _survival(logits)
 
 
 def risk(logits: torch.Tensor) -> torch.Tensor:

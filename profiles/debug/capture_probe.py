@@ -17,8 +17,26 @@ x = torch.randn(B * N, 512, device=dev).bfloat16()
 cu = torch.arange(0, (B + 1) * N, N, dtype=torch.int32, device=dev)
 batch = {"x_packed": x, "cu_seqlens": cu, "max_len": N, "omic": torch.rand(B, 3354, device=dev), "patient_id": None}
 y = torch.randint(0, 4, (B,), device=dev); c = torch.randint(0, 2, (B,), device=dev)
+tok = torch.randn(B, 7, 256, device=dev, requires_grad=True)
+tokp = torch.randn(B, 33, 256, device=dev, requires_grad=True)
+from imp_b200 import token_tail as TT
+def pinv_only():
+    a = torch.softmax(tok @ tok.transpose(1, 2), dim=-1)
+    return TT.iterative_pinv(a).sum()
+def nystrom_noconv():
+    m = model.path_decoder.attn
+    old = m.residual; m.residual = False
+    try:
+        return m(tok).sum()
+    finally:
+        m.residual = old
 stages = {
   "hot": lambda: (imp_b200.model.IMPHotPath.forward(model, batch)["p_proto"]).sum(),
+  "pinv": pinv_only,
+  "nystrom_noconv": nystrom_noconv,
+  "translayer": lambda: model.path_decoder(tok).sum(),
+  "bottleattn": lambda: model.bottleattn(tokp, tok)[0].sum(),
+  "tail_eval_like": lambda: model._fuse_and_classify(tokp, tok, None).sum(),
   "full": lambda: (lambda out: survival.nll_loss_new(out, y, c) + out[5] + out[1])(model(batch)),
 }
 for name, fn in stages.items():
@@ -29,6 +47,8 @@ for name, fn in stages.items():
         gs.close()
     except Exception:
         print(name, "capture FAILED")
-        traceback.print_exc()
-        torch.cuda.synchronize() if False else None
-        break
+        print(traceback.format_exc().splitlines()[-12:])
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
