@@ -219,6 +219,50 @@ def gen_model_full(seed):
     npz("model_P6_full.npz", **arrs)
 
 
+def gen_umeml(seed):
+    """The non-GAN UMEML (models/umeml.py:83-221), one slide per batch as the reference requires: eval logits, the
+    train pair (logits, modular_loss) and gradients incl. the learnable prototypes."""
+    import importlib
+    import json
+    from types import SimpleNamespace as NS
+    from util_hotpath import fill_state
+    R.load_model_module()
+    mod = importlib.import_module("medmm.modeling.models.umeml")
+    cfg = NS(DATASET=NS(ROOT=".", PATH=NS(DIM=512), OMIC=NS(DIM=1000)),
+             MODEL=NS(DROPOUT=0.0, HIDDEN_DIM=256, PROJECT_DIM=256, FUSION="concat", SIZE="small", UMEML=NS(PROTOTYPES=6, REGISTERS=3)))
+    torch.manual_seed(seed)
+    model = mod.UMEML(cfg, num_classes=4, omic_sizes=1000).float()
+    fill_state(model, seed)
+    with torch.no_grad():
+        model.p_proto.uniform_(-1.0 / 6, 1.0 / 6, generator=torch.Generator().manual_seed(seed + 3))
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    g = torch.Generator().manual_seed(seed + 1)
+    img = torch.randn(1, 200, 512, generator=g)
+    omic = torch.rand(1, 1000, generator=g)
+    arrs = {"img": img, "omic": omic, "param_seed": seed, "p_proto": model.p_proto.detach().clone(),
+            "state_keys": np.array(json.dumps({k: list(v.shape) for k, v in model.state_dict().items()}))}
+    model.eval()
+    with torch.no_grad(), R.cpu_cuda_noop():
+        arrs["eval.logits"] = model({"img": img, "omic": omic})
+    model.train()
+    with R.cpu_cuda_noop():
+        logits, modular = model({"img": img, "omic": omic})
+    loss = logits.square().sum() + modular
+    loss_nomod = logits.square().sum()
+    names = ("p_proto", "path_net.0.weight", "omic_net.0.weight", "classifier.weight", "bottleattn.bottle_tokens")
+    loss_nomod.backward(retain_graph=True)
+    for k in names:
+        arrs["train.grad_nomod." + k] = dict(model.named_parameters())[k].grad.clone()
+    model.zero_grad()
+    loss.backward()
+    arrs.update({"train.logits": logits, "train.modular_loss": modular})
+    for k in names:
+        arrs["train.grad." + k] = dict(model.named_parameters())[k].grad.clone()
+    npz("umeml_P6_N200.npz", **arrs)
+
+
 def gen_distance(seed):
     """euclidean_squared_distance (metrics/distance.py:46-61): the only reference arithmetic behind A9."""
     dist = R.load_distance()
@@ -238,4 +282,5 @@ if __name__ == "__main__":
     gen_chain(mod, ops, 16, 384, 5)
     gen_model(6)
     gen_model_full(8)
+    gen_umeml(9)
     gen_distance(7)

@@ -130,3 +130,44 @@ def test_p32_model_runs_a_training_step(tmp_path, monkeypatch):
         missing = [k for k, p in model.named_parameters() if p.grad is None and not k.startswith(("gan_", "g_omic_net"))]
         assert not missing, missing
         assert all(torch.isfinite(p.grad).all().item() for p in model.parameters() if p.grad is not None)
+
+
+def test_umeml_matches_reference():
+    """The non-GAN variant on the same kernels: eval logits, (logits, modular_loss) in train, gradients
+    incl. the learnable prototypes, against the executed reference (tests/golden/umeml_P6_N200.npz)."""
+    from imp_b200.registry import build_model
+    import imp_b200.umeml  # noqa: F401
+    from util_hotpath import fill_state
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "umeml_P6_N200.npz"))
+    z = {k: torch.from_numpy(z[k]) if z[k].dtype.kind in "fiu" else z[k] for k in z.files}
+    cfg = make_cfg()
+    cfg.DATASET.OMIC.DIM = 1000
+    dev = "cuda"
+    model = build_model("umeml", verbose=False, cfg=cfg, num_classes=4, omic_sizes=1000)
+    fill_state(model, int(z["param_seed"]))
+    with torch.no_grad():
+        model.p_proto.copy_(z["p_proto"])
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    model = model.to(dev)
+    batch = {"img": z["img"].to(dev), "omic": z["omic"].to(dev)}
+    L = Ledger("drop-in umeml (non-GAN, P=6, N=200)")
+    with torch.no_grad():
+        L.add("eval logits", rel(model.eval()(batch), z["eval.logits"]), 1e-3, "executed reference")
+    logits, modular = model.train()(batch)
+    L.add("train logits", rel(logits, z["train.logits"]), 1e-3, "executed reference")
+    ref = z["train.modular_loss"].item()
+    L.add("modular_loss", abs(modular.item() - ref) / abs(ref), 2e-2, "executed reference", "200 random patches: conditioning under bf16 storage of h")
+    named = dict(model.named_parameters())
+    names = ("p_proto", "path_net.0.weight", "omic_net.0.weight", "classifier.weight", "bottleattn.bottle_tokens")
+    logits.square().sum().backward(retain_graph=True)
+    for k in names:
+        L.add("grad(logits^2) " + k, rel(named[k].grad, z["train.grad_nomod." + k]), 6e-2 if k.startswith("path_net") else 5e-3,
+              "executed reference", "ReLU mask flips from rounding the fp32 fixture to bf16" if k.startswith("path_net") else "")
+    model.zero_grad()
+    (logits.square().sum() + modular).backward()
+    for k in names:
+        L.add("grad(logits^2 + modularity) " + k, rel(named[k].grad, z["train.grad." + k]), 1.5e-1, "executed reference",
+              "conditioning of the small-bag modularity gradient")
+    L.assert_ok()

@@ -198,3 +198,18 @@ def test_survival_loss_and_risk_match_reference_formulas():
            - c.view(-1, 1) * torch.log(Sp.gather(1, y.view(-1, 1) + 1).clamp(min=1e-7))).mean()
     assert abs(survival.nll_loss_new((logits,), y, c).item() - ref.item()) < 1e-6
     assert torch.allclose(survival.risk(logits), O.survival_risk(logits), atol=1e-6)
+
+
+def test_umeml_registry_and_state_dict_contract():
+    """The non-GAN ``umeml`` (models/umeml.py:83-221): same registry name, same state_dict keys and shapes, p_proto a
+    Parameter."""
+    from imp_b200.registry import build_model
+    import imp_b200.umeml  # noqa: F401
+    z = np.load(os.path.join(G, "umeml_P6_N200.npz"))
+    cfg = make_cfg()
+    cfg.DATASET.OMIC.DIM = 1000
+    model = build_model("umeml", verbose=False, cfg=cfg, num_classes=4, omic_sizes=1000)
+    ref = json.loads(str(z["state_keys"]))
+    mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert mine == ref, (sorted(set(ref) ^ set(mine)), {k: (mine.get(k), ref.get(k)) for k in ref if mine.get(k) != ref.get(k)})
+    assert isinstance(model.p_proto, torch.nn.Parameter)
