@@ -93,10 +93,48 @@ def softmax_pool(h: torch.Tensor, cu_seqlens: torch.Tensor, max_len: int, qt: to
 # ------------------------------------------------------------------------------------------
 # fused hot path: path_net + stacked prototype blocks (umeml_gan.py:410,425-434)
 # ------------------------------------------------------------------------------------------
+def _block_forward(c, pooled_fn, in_w, in_b, out_w, out_b, ln_w, ln_b):
+    """One prototype block on tokens c (B|1,P,D) with every intermediate the hand-derived backward needs.
+    ``pooled_fn(q~) -> (pooled, lse)`` is the pooling kernel (plus the cross-rank merge in giant-bag mode)."""
+    d = c.shape[-1]
+    q = F.linear(c, in_w[:d], None if in_b is None else in_b[:d]) * (float(d) ** -0.5)      # attention.py:368,432
+    qt = (q @ in_w[d:2 * d]).contiguous()                                                     # folded key projection
+    pooled, lse = pooled_fn(qt)
+    v = F.linear(pooled, in_w[2 * d:], None if in_b is None else in_b[2 * d:])               # :382 (value half), :530
+    o = F.linear(v, out_w, out_b)                                                             # :533
+    y, mean, rstd = torch.native_layer_norm(o, (d,), ln_w, ln_b, 1e-5)                        # umeml_gan.py:79
+    return c + y, dict(c=c, q=q, qt=qt, pooled=pooled, lse=lse, v=v, o=o, mean=mean, rstd=rstd)
+
+
+def _block_tail_backward(g_c, sv, in_w, out_w, ln_w, ln_b):
+    """Cotangent g_c of the block output -> (dpooled, d c_in through the residual, parameter gradients of the tail)."""
+    d = g_c.shape[-1]
+    do, dln_w, dln_b = torch.ops.aten.native_layer_norm_backward(g_c, sv["o"], [d], sv["mean"], sv["rstd"], ln_w, ln_b, [True, True, True])
+    do2, v2 = do.reshape(-1, d), sv["v"].reshape(-1, d)
+    dv = do2 @ out_w
+    grads = {"out_w": do2.t() @ v2, "out_b": do2.sum(0), "ln_w": dln_w, "ln_b": dln_b,
+             "wv": dv.t() @ sv["pooled"].reshape(-1, d), "bv": dv.sum(0)}
+    dpooled = (dv @ in_w[2 * d:]).view_as(sv["pooled"])
+    return dpooled, grads
+
+
+def _fold_backward(dqt, sv, in_w):
+    """Cotangent of the folded queries q~ (same batch shape as c_in) -> (d c_in, dWq, dbq, dWk)."""
+    d = dqt.shape[-1]
+    scale = float(d) ** -0.5
+    dqt2, q2, c2 = dqt.reshape(-1, d), sv["q"].reshape(-1, d), sv["c"].reshape(-1, d)
+    dpre = (dqt2 @ in_w[d:2 * d].t()) * scale
+    return (dpre @ in_w[:d]).view_as(sv["c"]), dpre.t() @ c2, dpre.sum(0), q2.t() @ dqt2
+
+
 class _ProtoFusionFn(torch.autograd.Function):
     """inputs: x (R,512) bf16 packed, cu (B+1) int32, max_len, p_drop, seed, p_proto (1|B,P,256),
     w1, b1, then 6 tensors per block (in_proj_weight, in_proj_bias, out_proj.weight,
-    out_proj.bias, norm1.weight, norm1.bias).  Returns (c (B,P,256) fp32, h (R,256) bf16)."""
+    out_proj.bias, norm1.weight, norm1.bias).  Returns (c (B,P,256) fp32, h (R,256) bf16).
+
+    The P x 256 token algebra between the kernels (query fold, value / output projection, LayerNorm, residual) is
+    evaluated with its intermediates kept, and differentiated by hand in ``backward``: about a dozen batched GEMMs per
+    block instead of the ~100 small kernels per block an autograd graph over the same expressions launches."""
 
     @staticmethod
     def forward(ctx, x, cu, max_len, p_drop, seed, shard_group, p_proto, w1, b1, *blk):
@@ -106,20 +144,23 @@ class _ProtoFusionFn(torch.autograd.Function):
         nb = cu.numel() - 1
         h = kernels.pathnet_fwd(x, kernels.cast_bf16(w1.detach().contiguous()), b1.detach().contiguous(),
                                 p_drop, seed)
+
+        def pooled_fn(qt):
+            pooled, lse = kernels.pool_fwd(h, cu, max_len, qt)
+            if shard_group is not None:          # giant bag sharded over ranks: LSE merge of the partial states
+                pooled, lse = parallel.merge_shards(pooled, lse, shard_group)
+            return pooled, lse
+
         c = p_proto.detach()
         saved = []
         with torch.no_grad():
             for k in range(nblk):
-                in_w, in_b, out_w, out_b, ln_w, ln_b = blk[6 * k:6 * k + 6]
-                qt = fold_query(c, in_w, in_b).contiguous()
-                pooled, lse = kernels.pool_fwd(h, cu, max_len, qt)
-                if shard_group is not None:          # giant bag sharded over ranks: LSE merge of the partial states
-                    pooled, lse = parallel.merge_shards(pooled, lse, shard_group)
-                c = block_tail(c, pooled, in_w, in_b, out_w, out_b, ln_w, ln_b)
-                saved += [pooled, lse]
+                c, sv = _block_forward(c, pooled_fn, *blk[6 * k:6 * k + 6])
+                saved.append(sv)
         if c.shape[0] != nb:
             c = c.expand(nb, -1, -1)
-        ctx.save_for_backward(x, h, cu, p_proto, w1, b1, *blk, *saved)
+        ctx.save_for_backward(x, h, cu, w1, b1, *blk)
+        ctx.block_saved = saved
         ctx.nblk, ctx.max_len, ctx.p_drop, ctx.shard_group = nblk, max_len, p_drop, shard_group
         ctx.mark_non_differentiable(h)
         return c.contiguous(), h
@@ -128,63 +169,66 @@ class _ProtoFusionFn(torch.autograd.Function):
     def backward(ctx, dc, _dh_unused):
         nblk = ctx.nblk
         t = ctx.saved_tensors
-        x, h, cu, p_proto, w1, b1 = t[:6]
-        blk = t[6:6 + 6 * nblk]
-        saved = t[6 + 6 * nblk:]
-        dc = dc.contiguous()
-        # rebuild the tiny token graph with autograd; the pooled tokens are leaves
-        with torch.enable_grad():
-            p_leaf = p_proto.detach().requires_grad_(True)
-            w_leaf = [w.detach().requires_grad_(True) for w in blk]
-            pooled_leaf = [saved[2 * k].detach().requires_grad_(True) for k in range(nblk)]
-            c = p_leaf
-            qts = []
-            for k in range(nblk):
-                in_w, in_b, out_w, out_b, ln_w, ln_b = w_leaf[6 * k:6 * k + 6]
-                qts.append(fold_query(c, in_w, in_b))
-                c = block_tail(c, pooled_leaf[k], in_w, in_b, out_w, out_b, ln_w, ln_b)
-        lses = [saved[2 * k + 1] for k in range(nblk)]
-        qts_c = [q.detach().contiguous() for q in qts]
-        keep_scale = 1.0 / (1.0 - ctx.p_drop) if ctx.p_drop > 0 else 1.0
+        x, h, cu, w1, b1 = t[:5]
+        blk = t[5:5 + 6 * nblk]
+        saved = ctx.block_saved
+        keep_scale = 1.0
         if ctx.p_drop > 0:   # the kernel keeps an element iff its 16 hash bits >= round(65536 p): match its scale
             thr = int(ctx.p_drop * 65536.0 + 0.5)
             keep_scale = 65536.0 / (65536.0 - thr) if thr else 1.0
-
-        outs, gouts = [c], [dc]          # running list of (tensor, cotangent) pairs of the token graph
+        d = D
+        g_c = dc.contiguous()                 # cotangent of the current block's output, (B,P,D)
+        qts = [sv["qt"] for sv in saved]
+        lses = [sv["lse"] for sv in saved]
         dpool: List[Optional[torch.Tensor]] = [None] * nblk
         delta: List[Optional[torch.Tensor]] = [None] * nblk
-        dq_last = None
+        par: List[Optional[dict]] = [None] * nblk
         db1 = torch.empty(D, device=x.device, dtype=torch.float32)
         dz = None
+        d_proto = None
         for k in reversed(range(nblk)):
-            (g,) = torch.autograd.grad(outs, [pooled_leaf[k]], gouts, retain_graph=True)
-            dpool[k] = g.contiguous()
-            delta[k] = (_bf16_round(dpool[k]) * pooled_leaf[k].detach()).sum(-1).contiguous()
+            in_w, in_b, out_w, out_b, ln_w, ln_b = blk[6 * k:6 * k + 6]
+            sv = saved[k]
+            if g_c.shape[0] != sv["pooled"].shape[0]:
+                g_c = g_c.expand(sv["pooled"].shape[0], -1, -1)
+            dp, grads = _block_tail_backward(g_c.contiguous(), sv, in_w, out_w, ln_w, ln_b)
+            dpool[k] = dp.contiguous()
+            delta[k] = (_bf16_round(dpool[k]) * sv["pooled"]).sum(-1).contiguous()
             if k > 0:
-                dq, _ = kernels.pool_bwd(h, cu, ctx.max_len, [qts_c[k]], [dpool[k]], [lses[k]], [delta[k]], 0,
-                                         want_dz=False)
+                dq, _ = kernels.pool_bwd(h, cu, ctx.max_len, [qts[k]], [dpool[k]], [lses[k]], [delta[k]], 0, want_dz=False)
             else:
-                dq, dz = kernels.pool_bwd(h, cu, ctx.max_len, qts_c, dpool, lses, delta, 0, want_dz=True,
+                dq, dz = kernels.pool_bwd(h, cu, ctx.max_len, qts, dpool, lses, delta, 0, want_dz=True,
                                           relu_mask=True, keep_scale=keep_scale, db1=db1)
             if ctx.shard_group is not None:       # every rank saw only its patches: sum the partial dq~
                 parallel.allreduce_sum_(dq, ctx.shard_group)
-            if qts[k].shape[0] == 1 and dq.shape[0] != 1:
+            shared = sv["c"].shape[0] == 1 and dq.shape[0] != 1
+            if shared:
                 dq = dq.sum(0, keepdim=True)
-            outs.append(qts[k])
-            gouts.append(dq)
-        leaves = [p_leaf] + w_leaf
-        grads = torch.autograd.grad(outs, leaves, gouts, allow_unused=True)
+            dc_in, dwq, dbq, dwk = _fold_backward(dq, sv, in_w)
+            grads.update(wq=dwq, bq=dbq, wk=dwk)
+            par[k] = grads
+            # cotangent of this block's input tokens: residual path + query path
+            g_prev = g_c.sum(0, keepdim=True) if shared else g_c
+            g_c = g_prev + dc_in
+        d_proto = g_c
         dw1 = kernels.pathnet_dw(dz, x)
         if ctx.shard_group is not None:
             parallel.allreduce_sum_(dw1, ctx.shard_group)
             parallel.allreduce_sum_(db1, ctx.shard_group)
         need = ctx.needs_input_grad
         res = [None, None, None, None, None, None,
-               grads[0] if need[6] else None,
+               d_proto if need[6] else None,
                dw1.to(w1.dtype) if need[7] else None,
                db1.to(b1.dtype) if need[8] else None]
-        for i in range(6 * nblk):
-            res.append(grads[1 + i] if need[9 + i] else None)
+        for k in range(nblk):
+            g = par[k]
+            in_b = blk[6 * k + 1]
+            res += [torch.cat([g["wq"], g["wk"], g["wv"]], dim=0) if need[9 + 6 * k] else None,
+                    (torch.cat([g["bq"], torch.zeros_like(g["bq"]), g["bv"]]) if (in_b is not None and need[10 + 6 * k]) else None),
+                    g["out_w"] if need[11 + 6 * k] else None,
+                    g["out_b"] if need[12 + 6 * k] else None,
+                    g["ln_w"] if need[13 + 6 * k] else None,
+                    g["ln_b"] if need[14 + 6 * k] else None]
         return tuple(res)
 
 
