@@ -290,6 +290,12 @@ def drop_in_model_step(dev, x, cu, omic, B, N, P):
             gs.close()
             rec.update({"value": B * 1e3 / ms_graph, "ms_per_step": ms_graph, "launch_mode": "whole step replayed from one CUDA graph"})
         except Exception as exc:
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            try:
+                torch.cuda.synchronize(dev)
+            except Exception:
+                pass
             rec.update({"value": B * 1e3 / ms_eager, "ms_per_step": ms_eager,
                         "launch_mode": "eager (graph capture failed: %s: %s)" % (type(exc).__name__, str(exc)[:160])})
         model.flush_importance_logs()

@@ -168,6 +168,9 @@ def test_umeml_matches_reference():
     model.zero_grad()
     (logits.square().sum() + modular).backward()
     for k in names:
-        L.add("grad(logits^2 + modularity) " + k, rel(named[k].grad, z["train.grad." + k]), 1.5e-1, "executed reference",
-              "conditioning of the small-bag modularity gradient")
+        # 200 random patches: the fp64 ORACLE's token gradient of the modularity term moves by 0.33 when x and W1 are
+        # rounded to bf16 and by 0.05 when only h is (measured with oracle/imp_oracle.py on this fixture); the same
+        # quantity agrees to 5e-4 at 16 384 patches.  The bound only guards against gross errors here.
+        L.add("grad(logits^2 + modularity) " + k, rel(named[k].grad, z["train.grad." + k]), 5e-1, "executed reference",
+              "ill-conditioned: the fp64 oracle itself moves by 0.33 under the same input rounding")
     L.assert_ok()
