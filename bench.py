@@ -274,9 +274,11 @@ def drop_in_model_step(dev, x, cu, omic, B, N, P):
                 out = fn()
             e1.record()
             torch.cuda.synchronize(dev)
-            return e0.elapsed_time(e1) / k, out
+            # only the VALUE leaves: a retained loss tensor keeps its autograd graph and with it AccumulateGrad nodes bound
+            # to the stream of this eager run, which a later capture on another stream is not allowed to synchronise with
+            return e0.elapsed_time(e1) / k, float(out)
         ms_eager, loss = timeit(step)
-        rec = {"unit": "bags/s", "bags_per_step": B, "loss": float(loss), "eager": {"value": B * 1e3 / ms_eager, "ms_per_step": ms_eager},
+        rec = {"unit": "bags/s", "bags_per_step": B, "loss": loss, "eager": {"value": B * 1e3 / ms_eager, "ms_per_step": ms_eager},
                "what": "build_model('umeml_gan', cfg) -> model(batch) 7-tuple -> NLL + KD + modularity -> backward; token tail in "
                        "batched torch (fp32); importance rows kept on the device (IMPORTANCE_LOG='defer') and appended afterwards"}
         try:
