@@ -50,3 +50,20 @@ def test_sentinel_strip_live_semantics():
     x[7, 5] = -10000.0
     idx = torch.nonzero(x == -10000)
     assert int(idx[0][0]) == O.bag_length(x) == 7
+
+
+def test_register_into_the_reference_registry():
+    """INTEGRATION.md option 0: ``register_into(MODEL_REGISTRY)`` puts this repo's factories under the reference's own
+    registry names, and the reference's ``build_model`` then returns the B200 model class."""
+    R.load_model_module()
+    import importlib
+    build = importlib.import_module("medmm.modeling.models.build")
+    from imp_b200.registry import register_into
+    from imp_b200.umeml_gan import UMEML_GAN
+    register_into(build.MODEL_REGISTRY)
+    assert {"umeml_gan", "umeml"} <= set(build.MODEL_REGISTRY.registered_names())
+    from types import SimpleNamespace as NS
+    cfg = NS(DATASET=NS(ROOT=".", PATH=NS(DIM=512), OMIC=NS(DIM=3354)),
+             MODEL=NS(DROPOUT=0.25, HIDDEN_DIM=256, PROJECT_DIM=256, FUSION="concat", SIZE="small", UMEML=NS(PROTOTYPES=6, REGISTERS=3)))
+    model = build.build_model("umeml_gan", verbose=False, cfg=cfg, num_classes=4, omic_sizes=1000)
+    assert isinstance(model, UMEML_GAN)
