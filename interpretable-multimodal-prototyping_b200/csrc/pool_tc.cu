@@ -5,7 +5,7 @@
 // One kernel, two modes, per 128-row tile of h (R,256) bf16 (TMA, 128-byte swizzle):
 //   MMA1  S[n][c]      = sum_f h[n][f] G[c][f]          M 128 (patch rows), N = PP (fwd: q~) or 2 PP (dq: [q~ ; dpooled]),
 //                                                        K 256; A = the h tile (K-major), B = G (K-major)
-//   epilogue (thread = patch row = TMEM lane, 4 warps)
+//   epilogue (8 warps: thread = patch row = TMEM lane x one half of the prototype columns)
 //         fwd : w[n][p]  = exp2(S log2e - m_p)           m_p = the CTA's running reference maximum (see below)
 //         dq  : w[n][p]  = a (dA - delta_p),  a = exp2(S log2e - lse_p log2e)
 //         -> bf16, written as the MN-major B operand of MMA2 ([128 rows n][64 p], one 128-byte row per patch)
@@ -24,7 +24,9 @@
 // maximum over the bag's earlier tiles).  The partial state a CTA leaves is (m_p, l_p, acc_p) like the mma.sync
 // kernel it replaces, merged across the CTAs of a bag by pool_merge / reduce_dq (pool.cu).
 //
-// Warps: 0-3 epilogue, 4 TMA producer, 5 MMA issuer.  The issuer polls its barriers instead of waiting in a fixed
+// Warps: 0-7 epilogue (with 4 the per-tile work of ~700 dependent instructions sat on one warp per scheduler and
+// took ~2100 cycles; two warps per scheduler halve the columns per thread and hide each other's latencies),
+// 8 TMA producer, 9 MMA issuer.  The issuer polls its barriers instead of waiting in a fixed
 // order: MMA1 of tile t+1 goes out as soon as its h tile has landed (S is double buffered in TMEM), MMA2 of tile t as
 // soon as w is written -- a blocking wait for the NEXT tile's load in front of MMA2(t) kept the stage of tile t, and with
 // it the load of tile t+2, hostage (one load in flight per SM: 2.9 us per tile, first version).  The forward with
@@ -38,7 +40,10 @@ constexpr int kD = 256;
 constexpr int kTM = 128;                        // patch rows per tile
 constexpr int kTile = kTM * kD * 2;             // 64 KB: four [128 rows][64 feats] boxes
 constexpr int kBox = kTM * 128;                 // 16 KB
-constexpr int kThreads = 6 * 32;
+constexpr int kEpiWarps = 8;                    // (TMEM lane quarter) x (column half)
+constexpr int kTmaWarp = 8, kMmaWarp = 9;
+constexpr int kThreads = 10 * 32;
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kWBox = kTM * 128;                // one w buffer: [128 rows][64 p] bf16
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -112,8 +117,8 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
   uint64_t* full = bars + 14;       // [kStages] TMA -> MMA1
   uint64_t* empty = bars + 17;      // [kStages] MMA2 retired -> TMA
   uint64_t* sfull = bars + 4;       // [2] MMA1 -> epilogue
-  uint64_t* sempty = bars + 6;      // [2] 4 warps -> MMA1 (S in registers)
-  uint64_t* wfull = bars + 8;       // [2] 4 warps -> MMA2 (w written, acc rescaled)
+  uint64_t* sempty = bars + 6;      // [2] 8 warps -> MMA1 (S in registers)
+  uint64_t* wfull = bars + 8;       // [2] 8 warps -> MMA2 (w written, acc rescaled)
   uint64_t* wempty = bars + 10;     // [2] MMA2 retired -> epilogue (w buffer reusable)
   uint64_t* accdone = bars + 12;    // MMA2 of a tile retired (slow path: at most one phase behind, see there)
   uint64_t* alldone = bars + 13;    // MMA2 of the CTA's LAST tile retired (single phase)
@@ -135,26 +140,26 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
     }
     return;
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tm_h);
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 4); mbar_init(&wfull[i], 4); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], 1); mbar_init(&sempty[i], kEpiWarps); mbar_init(&wfull[i], kEpiWarps); mbar_init(&wempty[i], 1); }
     mbar_init(accdone, 1);
     mbar_init(alldone, 1);
     mbar_fence_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();                               // barriers initialised, TMEM allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_s0 = tmem_base, tm_acc = tmem_base + 256;   // S: 2 x N1 <= 256 columns; acc: 2 x 64
-  if (warp != 4) {
+  if (warp != kTmaWarp) {
     // The h tiles are already on their way (the TMA warp below does not wait for this): stage G and the small tables
-    // with the other five warps.  Loads are issued four deep -- a load -> pack -> store chain per item made this
+    // with the other nine warps.  Loads are issued four deep -- a load -> pack -> store chain per item made this
     // prologue 10 % of the kernel (one L2 round trip per iteration).
-    const int tid = warp == 5 ? 128 + lane : threadIdx.x;       // 160 workers
-    constexpr int kWorkers = 160, kItems = N1 * 64;
+    const int tid = warp == kMmaWarp ? kEpiThreads + lane : threadIdx.x;       // 288 workers
+    constexpr int kWorkers = kEpiThreads + 32, kItems = N1 * 64;
     for (int base = tid; base < kItems; base += 4 * kWorkers) {
       float4 v[4];
 #pragma unroll
@@ -193,7 +198,7 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
     bar_sync(3, kWorkers);
   }
 
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       for (int i = 0; i < ntiles; ++i) {
@@ -206,7 +211,7 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
           tma_load_2d(dst + bx * kBox, &tm_h, &full[stage], bx * 64, row_begin + (t0 + i) * kTM);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc1 = umma_idesc_bf16(kTM, N1, 0, 0);
@@ -256,52 +261,56 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
     }
   } else {
     // ------------------------------ epilogue warps ------------------------------
-    const int n = warp * 32 + lane;                       // row inside the tile = TMEM lane
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    constexpr int CH = PP / 2;                            // prototype columns per thread
+    const int q = warp & 3, hf = warp >> 2;
+    const int n = q * 32 + lane;                          // row inside the tile = TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int col0 = hf * CH;
+    const int mycol = col0 + (lane & (CH - 1));           // fwd: the column whose partial normaliser this lane keeps
     uint8_t* wrow_base = s_w + n * 128;
-    float lpart[PP / 32];                                 // fwd: lane l holds this warp's sum of column l (+32)
-#pragma unroll
-    for (int c = 0; c < PP / 32; ++c) lpart[c] = 0.f;
+    float lpart = 0.f;
+    auto ld_cols = [&](uint32_t addr, uint32_t (&v)[CH]) {
+      if constexpr (CH == 16) tmem_ld16(addr, v); else tmem_ld32(addr, v);
+    };
     for (int i = 0; i < ntiles; ++i) {
       const int buf = i & 1, wb = i % NBUF;
       const bool row_ok = row_begin + (t0 + i) * kTM + n < row_end;
       mbar_wait(&sfull[buf], (i >> 1) & 1);
       tc_fence_after();
-      float w[PP];
+      float w[CH];
       if (MODE == MODE_FWD) {
-        float t[PP];
-#pragma unroll
-        for (int c0 = 0; c0 < PP; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tm_s0 + buf * N1 + lane_addr + c0, v);
+        float t[CH];
+        {
+          uint32_t v[CH];
+          ld_cols(tm_s0 + buf * N1 + lane_addr + col0, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) t[c0 + e] = row_ok ? __uint_as_float(v[e]) * kLog2e : -INFINITY;
+          for (int e = 0; e < CH; ++e) t[e] = row_ok ? __uint_as_float(v[e]) * kLog2e : -INFINITY;
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sempty[buf]);
         bool hit = false;
 #pragma unroll
-        for (int e = 0; e < PP; ++e) hit |= t[e] > s_m[e] + kLazy;
-        if (bar_or(1, 128, hit)) {
+        for (int e = 0; e < CH; ++e) hit |= t[e] > s_m[col0 + e] + kLazy;
+        if (bar_or(1, kEpiThreads, hit)) {
           // ---- slow path: new reference maxima, rescale of the accumulators ----
 #pragma unroll
-          for (int e = 0; e < PP; ++e) {
+          for (int e = 0; e < CH; ++e) {
             const float mx = warp_max(t[e]);
-            if (lane == (e & 31)) s_wmax[warp * 64 + e] = mx;
+            if (lane == (e & 31)) s_wmax[q * 64 + col0 + e] = mx;
           }
-          bar_sync(2, 128);
-          if (n < PP) {
-            const float mx = fmaxf(fmaxf(s_wmax[n], s_wmax[64 + n]), fmaxf(s_wmax[128 + n], s_wmax[192 + n]));
-            const float m_old = s_m[n];
+          bar_sync(2, kEpiThreads);
+          if (threadIdx.x < PP) {
+            const int c = threadIdx.x;
+            const float mx = fmaxf(fmaxf(s_wmax[c], s_wmax[64 + c]), fmaxf(s_wmax[128 + c], s_wmax[192 + c]));
+            const float m_old = s_m[c];
             const float m_new = fmaxf(m_old, mx);                       // finite: the tile has a valid row
-            s_alpha[n] = exp2f(m_old - m_new);                          // 0 on the first tile (m_old = -inf)
-            s_m[n] = m_new;
+            s_alpha[c] = exp2f(m_old - m_new);                          // 0 on the first tile (m_old = -inf)
+            s_m[c] = m_new;
           }
-          bar_sync(2, 128);
-#pragma unroll
-          for (int c = 0; c < PP / 32; ++c) lpart[c] *= s_alpha[c * 32 + lane];
+          bar_sync(2, kEpiThreads);
+          lpart *= s_alpha[mycol];
           if (i > 0) {
             // MMA2 of tile i-1 retired.  S of tile i exists, so MMA1(i) and everything issued before it, MMA2(i-2)
             // included, has completed (the tensor pipe retires in issue order): accdone has seen i-1 or i commits and
@@ -309,70 +318,63 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
             mbar_wait(accdone, (i - 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int r = 0; r < 2; ++r) {                               // acc half 0, acc half 1
-#pragma unroll 1
-              for (int c0 = 0; c0 < PP; c0 += 32) {
-                uint32_t v[32];
-                const uint32_t addr = tm_acc + r * 64 + lane_addr + c0;
-                tmem_ld32(addr, v);
-                tmem_ld_wait();
+            for (int c0 = 0; c0 < PP; c0 += 32) {                       // this warp's quarter of acc half `hf`
+              uint32_t v[32];
+              const uint32_t addr = tm_acc + hf * 64 + lane_addr + c0;
+              tmem_ld32(addr, v);
+              tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * s_alpha[c0 + e]);
-                tmem_st32(addr, v);
-              }
+              for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * s_alpha[c0 + e]);
+              tmem_st32(addr, v);
             }
             tmem_st_wait();
             tc_fence_before();
           }
         }
 #pragma unroll
-        for (int e = 0; e < PP; ++e) w[e] = exp2f(t[e] - s_m[e]);
+        for (int e = 0; e < CH; ++e) w[e] = exp2f(t[e] - s_m[col0 + e]);
       } else {
+        uint32_t sv[CH], av[CH];
+        ld_cols(tm_s0 + buf * N1 + lane_addr + col0, sv);
+        ld_cols(tm_s0 + buf * N1 + lane_addr + PP + col0, av);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c0 = 0; c0 < PP; c0 += 32) {
-          uint32_t sv[32], av[32];
-          tmem_ld32(tm_s0 + buf * N1 + lane_addr + c0, sv);
-          tmem_ld32(tm_s0 + buf * N1 + lane_addr + PP + c0, av);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float a = row_ok ? exp2f(__uint_as_float(sv[e]) * kLog2e - s_m[c0 + e]) : 0.f;
-            w[c0 + e] = a * (__uint_as_float(av[e]) - s_alpha[c0 + e]);
-          }
+        for (int e = 0; e < CH; ++e) {
+          const float a = row_ok ? exp2f(__uint_as_float(sv[e]) * kLog2e - s_m[col0 + e]) : 0.f;
+          w[e] = a * (__uint_as_float(av[e]) - s_alpha[col0 + e]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sempty[buf]);
       }
-      uint32_t pk[PP / 2];
+      uint32_t pk[CH / 2];
 #pragma unroll
-      for (int e = 0; e < PP / 2; ++e) pk[e] = pack_bf16x2(w[2 * e], w[2 * e + 1]);
+      for (int e = 0; e < CH / 2; ++e) pk[e] = pack_bf16x2(w[2 * e], w[2 * e + 1]);
       if (MODE == MODE_FWD) {
-        // normaliser from the ROUNDED weights: transposing butterfly, 31 shuffles per 32 columns, lane l ends with column l
+        // normaliser from the ROUNDED weights: transposing butterfly over the warp's 32 rows; lane l ends with the sum of
+        // column (l mod CH) (CH = 16: 15 shuffles + one across the two half-warps; CH = 32: 31 shuffles)
+        float v[CH];
 #pragma unroll
-        for (int c = 0; c < PP / 32; ++c) {
-          float v[32];
+        for (int e = 0; e < CH / 2; ++e) { v[2 * e] = bf16lo(pk[e]); v[2 * e + 1] = bf16hi(pk[e]); }
 #pragma unroll
-          for (int e = 0; e < 16; ++e) { v[2 * e] = bf16lo(pk[c * 16 + e]); v[2 * e + 1] = bf16hi(pk[c * 16 + e]); }
+        for (int sft = CH / 2; sft >= 1; sft >>= 1) {
+          const bool up = (lane & sft) != 0;
 #pragma unroll
-          for (int sft = 16; sft >= 1; sft >>= 1) {
-            const bool up = (lane & sft) != 0;
-#pragma unroll
-            for (int j = 0; j < sft; ++j) {
-              const float send = up ? v[j] : v[j + sft];
-              const float keep = up ? v[j + sft] : v[j];
-              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
-            }
+          for (int j = 0; j < sft; ++j) {
+            const float send = up ? v[j] : v[j + sft];
+            const float keep = up ? v[j + sft] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
           }
-          lpart[c] += v[0];
         }
+        if (CH == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+        lpart += v[0];
       }
       // ---- w -> shared memory (MN-major B operand of MMA2), once the MMA2 that last read this buffer retired ----
       mbar_wait(&wempty[wb], ((i / NBUF) & 1) ^ 1);
       uint8_t* wrow = wrow_base + wb * kWBox;
 #pragma unroll
-      for (int c = 0; c < PP / 8; ++c)
-        *reinterpret_cast<uint4*>(wrow + ((c ^ (n & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      for (int c = 0; c < CH / 8; ++c)
+        *reinterpret_cast<uint4*>(wrow + ((((col0 >> 3) + c) ^ (n & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&wfull[wb]);
@@ -382,30 +384,27 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PoolTcParams p) {
     mbar_wait(alldone, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll 1
-      for (int c0 = 0; c0 < PP; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tm_acc + hf * 64 + lane_addr + c0, v);
-        tmem_ld_wait();
+    for (int c0 = 0; c0 < PP; c0 += 32) {                                 // feature half hf, features q*32 + lane
+      uint32_t v[32];
+      tmem_ld32(tm_acc + hf * 64 + lane_addr + c0, v);
+      tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) out_acc[(size_t)(c0 + e) * kD + hf * 128 + n] = __uint_as_float(v[e]);
-      }
+      for (int e = 0; e < 32; ++e) out_acc[(size_t)(c0 + e) * kD + hf * 128 + n] = __uint_as_float(v[e]);
     }
     if (MODE == MODE_FWD) {
       float* out_ml = p.part_ml + ((size_t)b * p.nsplit + split) * 2 * PP;
-#pragma unroll
-      for (int c = 0; c < PP / 32; ++c) s_wmax[warp * 64 + c * 32 + lane] = lpart[c];
-      bar_sync(2, 128);
-      if (n < PP) {
-        out_ml[n] = s_m[n] * kLn2;
-        out_ml[PP + n] = s_wmax[n] + s_wmax[64 + n] + s_wmax[128 + n] + s_wmax[192 + n];
+      if (lane < CH) s_wmax[q * 64 + mycol] = lpart;
+      bar_sync(2, kEpiThreads);
+      if (threadIdx.x < PP) {
+        const int c = threadIdx.x;
+        out_ml[c] = s_m[c] * kLn2;
+        out_ml[PP + c] = s_wmax[c] + s_wmax[64 + c] + s_wmax[128 + c] + s_wmax[192 + c];
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
