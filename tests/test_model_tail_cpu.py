@@ -213,3 +213,19 @@ def test_umeml_registry_and_state_dict_contract():
     mine = {k: list(v.shape) for k, v in model.state_dict().items()}
     assert mine == ref, (sorted(set(ref) ^ set(mine)), {k: (mine.get(k), ref.get(k)) for k in ref if mine.get(k) != ref.get(k)})
     assert isinstance(model.p_proto, torch.nn.Parameter)
+
+
+@pytest.mark.parametrize("n", [7, 14, 40, 127])
+def test_short_sequence_nystrom_equals_the_dense_form(n):
+    """token_tail.nystrom_short (block algebra on the m - n zero-padded tokens) against the literal padded 128 x 128
+    form (attention.py:46-161), outputs and gradients, in fp64."""
+    from imp_b200 import token_tail as T
+    torch.manual_seed(n)
+    att = T.NystromAttention(dim=256, dim_head=32, heads=8, num_landmarks=128, pinv_iterations=6, residual=True, dropout=0.0).double()
+    x = torch.randn(2, n, 256, dtype=torch.double, requires_grad=True)
+    w = torch.randn(256, dtype=torch.double)
+    y1, y2 = att(x), att.forward_dense(x)
+    g1 = torch.autograd.grad((y1 * w).sum(), [x] + list(att.parameters()))
+    g2 = torch.autograd.grad((y2 * w).sum(), [x] + list(att.parameters()))
+    assert rel(y1, y2) < 1e-12
+    assert max(rel(a, b) for a, b in zip(g1, g2)) < 1e-11
