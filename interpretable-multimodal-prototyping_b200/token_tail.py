@@ -64,7 +64,7 @@ def nystrom_short(q, k, v, m: int, iters: int):
     zsum = p * e0 + es.sum(-1, keepdim=True)
     cvec, dmat = e0 / zsum, es / zsum
     # initial scale 1 / (max row-abs-sum * max column-abs-sum) of the FULL m x m matrix, over the whole batch (utils.py:119-121)
-    rs = torch.maximum((p * cvec + dmat.sum(-1, keepdim=True)).max(), s.new_tensor((p + n) / m))
+    rs = (p * cvec + dmat.sum(-1, keepdim=True)).max().clamp_min((p + n) / m)      # padded rows sum to (p + n) / m = 1
     cs = torch.maximum((p / m + cvec.sum(-2)).max(), (p / m + dmat.sum(-2)).max())
     top = torch.cat([s.new_full(s.shape[:-2] + (1, 1), p / m), s.new_full(s.shape[:-2] + (1, n), rp / m)], dim=-1)
     mat = torch.cat([top, torch.cat([rp * cvec, dmat], dim=-1)], dim=-2)          # M(A), (B,H,n+1,n+1)
