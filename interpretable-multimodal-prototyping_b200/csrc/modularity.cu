@@ -256,6 +256,209 @@ __global__ void __launch_bounds__(256) modularity_prep_kernel(const PrepParams p
 }
 
 // ------------------------------------------------------------------------------------------
+// prep on tcgen05.  C = |x|^-1 (h . chat^T): h is EXACT in bf16 (it is stored that way), so with chat split into
+// hi + lo bf16 parts (chat - hi - lo ~ 2^-17 chat) the tensor core delivers the inner products to ~4e-6 relative --
+// far inside the 2^-12 log2 resolution of the fixed-point assignments -- as S = h [chat_hi ; chat_lo]^T (M 128,
+// N = 2 PTPAD, K 256, fp32 accumulation in TMEM).  One CTA per 128-row tile (two CTAs resident per SM): TMA brings the
+// h tile, the row threads take the norms from it while the MMAs run, the epilogue (thread = row = TMEM lane) writes the
+// fixed-point log2 assignments in the tiled layout (coalesced: for one slot a warp writes 32 consecutive rows), then the
+// tile is normalised in place and leaves as x_hat through coalesced stores; column sums of x_hat per bag by thread =
+// feature.  The fp32-FMA version this replaces spent 0.66 ms per 32 bags (14 % of HBM), bound by shared-memory reads.
+// ------------------------------------------------------------------------------------------
+constexpr int kPtThreads = 5 * 32;               // 4 row warps + 1 issuing warp
+template <int PTPAD>
+constexpr size_t prep_tc_smem() { return 1024 + (size_t)kABytes + (size_t)2 * PTPAD * 512 + 128 * 4 + 64; }
+
+template <int PTPAD>
+__global__ void __launch_bounds__(kPtThreads, 2)
+modularity_prep_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PrepParams p) {
+  constexpr int NB2 = 2 * PTPAD;                   // rows of the B operand: chat_hi slots, then chat_lo slots
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* s_h = smem;                             // [128 rows][256] bf16, four swizzled boxes
+  uint8_t* s_c = s_h + kABytes;                    // B operand: four boxes [NB2][64]
+  float* s_inv = reinterpret_cast<float*>(s_c + (size_t)NB2 * 512);   // [128] 1 / |x_row|
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_inv + 128);
+  uint64_t* full = bars;                           // TMA -> everyone
+  uint64_t* sfull = bars + 1;                      // MMA -> epilogue (one phase per bag of the tile)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = p.row_lo + blockIdx.x * kBM;
+  const int tile_end = min(r0 + kBM, p.row_hi);
+  const int data_end = __ldg(p.cu + p.B);          // rows past cu[B] belong to no bag
+  const int Pt = p.P1 + p.P2;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_h);
+      mbar_init(full, 1);
+      mbar_init(sfull, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 128);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 4 && elect_one()) {
+    mbar_arrive_expect_tx(full, kABytes);
+#pragma unroll
+    for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_h + bx * (kBM * 128), &tm_h, full, bx * 64, r0 - p.row_lo);
+  }
+  __syncwarp();
+
+  // ---- norms of the rows (thread = row), straight from the swizzled tile ----
+  const int n = threadIdx.x;                       // row inside the tile for warps 0-3
+  const int row = r0 + n;
+  float inv = 0.f;
+  bool neg = false;
+  if (warp < 4) {
+    mbar_wait(full, 0);
+    float ss = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < 32; ++c) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(s_h + (c >> 3) * (kBM * 128) + n * 128 + (((c & 7) ^ (n & 7)) << 4));
+      const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lo = bf16lo(wds[e]), hi = bf16hi(wds[e]);
+        ss = fmaf(lo, lo, fmaf(hi, hi, ss));
+        neg |= (lo < 0.f) || (hi < 0.f);
+      }
+    }
+    inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);          // F.normalize eps (utils.py:179,193)
+    s_inv[n] = inv;
+    if (row < tile_end) p.invn[row] = inv;
+    neg = neg && row < tile_end && row < data_end;
+    if (__any_sync(0xffffffffu, neg) && lane == 0) *p.negflag = 1;
+  }
+
+  // ---- per bag of the tile: B = [chat_hi ; chat_lo], MMA, fixed-point assignments ----
+  int b = find_segment(p.cu, p.B, r0);
+  int phase = 0;
+  for (; b < p.B; ++b) {
+    const int bag_lo = __ldg(p.cu + b);
+    if (bag_lo >= tile_end) break;
+    const int sa = max(bag_lo, r0), sb = min(__ldg(p.cu + b + 1), tile_end);
+    if (sa >= sb) continue;
+    __syncthreads();                               // the previous bag's MMAs have been consumed (epilogue below ends with the TMEM reads)
+    for (int i = threadIdx.x; i < PTPAD * 64; i += kPtThreads) {
+      const int slot = i >> 6, c = (i & 63) << 2;
+      int src = -1;
+      if (slot < p.P1) src = slot;
+      else if (slot >= p.P1pad && slot - p.P1pad < p.P2) src = p.P1 + slot - p.P1pad;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src >= 0) v = __ldg(reinterpret_cast<const float4*>(p.chat + ((size_t)b * Pt + src) * kD + c));
+      const uint32_t h01 = pack_bf16x2(v.x, v.y), h23 = pack_bf16x2(v.z, v.w);
+      const uint32_t l01 = pack_bf16x2(v.x - bf16lo(h01), v.y - bf16hi(h01)), l23 = pack_bf16x2(v.z - bf16lo(h23), v.w - bf16hi(h23));
+      const uint32_t boxo = (uint32_t)((c >> 6) * (NB2 * 128));
+      const uint32_t swz = (uint32_t)((c & 7) << 1);
+      const int rh = slot, rl = PTPAD + slot;
+      *reinterpret_cast<uint2*>(s_c + boxo + rh * 128 + ((((c & 63) >> 3) ^ (rh & 7)) << 4) + swz) = make_uint2(h01, h23);
+      *reinterpret_cast<uint2*>(s_c + boxo + rl * 128 + ((((c & 63) >> 3) ^ (rl & 7)) << 4) + swz) = make_uint2(l01, l23);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 4) {
+      mbar_wait(full, 0);
+      tc_fence_after();
+      if (elect_one()) {
+        constexpr uint32_t idesc = umma_idesc_bf16(kBM, NB2, 0, 0);
+        const uint32_t sh = smem_u32(s_h), sc = smem_u32(s_c);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) {
+          const uint64_t ad = umma_desc_sw128(sh + (k >> 2) * (kBM * 128) + (k & 3) * 32, 0, 1024);
+          const uint64_t bd = umma_desc_sw128(sc + (k >> 2) * (NB2 * 128) + (k & 3) * 32, 0, 1024);
+          umma_f16(tmem_base, ad, bd, idesc, k != 0);
+        }
+        umma_commit(sfull);
+      }
+      __syncwarp();
+    } else {
+      mbar_wait(sfull, phase);
+      tc_fence_after();
+      const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+      const bool mine = row >= sa && row < sb;
+#pragma unroll 1
+      for (int s0 = 0; s0 < PTPAD; s0 += 8) {
+        uint32_t vh[8], vl[8];
+        tmem_ld8(tmem_base + lane_addr + s0, vh);
+        tmem_ld8(tmem_base + lane_addr + PTPAD + s0, vl);
+        tmem_ld_wait();
+        if (mine) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int slot = s0 + e;
+            const float dot = (__uint_as_float(vh[e]) + __uint_as_float(vl[e])) * inv;
+            int fix = kNMax;                        // padding slots have zero tokens: dot == 0
+            if (dot > 0.f) fix = min(kNMax, max(0, __float2int_rn(((float)kCOff - log2f(dot)) * (float)(1 << kLogShift))));
+            // low 5 bits: token index inside its group (column-side operand); the row side masks them off
+            p.lfix[lfix_index(row, slot, PTPAD)] = (float)(fix * 32 + (slot < p.P1pad ? slot : slot - p.P1pad));
+          }
+        }
+      }
+      tc_fence_before();
+    }
+    phase ^= 1;
+  }
+  // rows of the tile that belong to no bag (past cu[B]: tile padding, or the unused tail of a buffer sized for the
+  // worst case) are masked in the sweep, but its loads must stay finite: 0 * NaN would poison the sums
+  if (warp < 4 && row >= data_end && row < ((p.R + kBM + kBN + 63) / 64) * 64) {
+    for (int slot = 0; slot < PTPAD; ++slot) p.lfix[lfix_index(row, slot, PTPAD)] = (float)(kNMax * 32);
+  }
+  __syncthreads();                                 // every MMA that reads the h tile has retired (the epilogues waited on sfull)
+  // ---- x_hat in place (bf16), column sums per bag, coalesced store ----
+  if (warp < 4) {
+    if (warp < 4) mbar_wait(full, 0);
+#pragma unroll 4
+    for (int c = 0; c < 32; ++c) {
+      uint4* ptr = reinterpret_cast<uint4*>(s_h + (c >> 3) * (kBM * 128) + n * 128 + (((c & 7) ^ (n & 7)) << 4));
+      const uint4 raw = *ptr;
+      const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2(bf16lo(wds[e]) * inv, bf16hi(wds[e]) * inv);
+      *ptr = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  __syncthreads();
+  if (warp < 4) {
+    const int nvalid = max(0, tile_end - r0);
+    for (int it = threadIdx.x; it < nvalid * 32; it += 128) {
+      const int r = it >> 5, c = (it & 31) << 3;
+      *reinterpret_cast<uint4*>(p.xh + (size_t)(r0 + r) * kD + c) =
+          *reinterpret_cast<const uint4*>(s_h + (c >> 6) * (kBM * 128) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4));
+    }
+    // column sums of the bf16-rounded unit rows, per bag (thread = 2 features)
+    int bb = find_segment(p.cu, p.B, r0);
+    for (; bb < p.B; ++bb) {
+      const int bag_lo = __ldg(p.cu + bb);
+      if (bag_lo >= tile_end) break;
+      const int sa = max(bag_lo, r0), sb = min(__ldg(p.cu + bb + 1), tile_end);
+      if (sa >= sb) continue;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int f = half * 128 + threadIdx.x;
+        float acc = 0.f;
+        for (int r = sa - r0; r < sb - r0; ++r)
+          acc += __bfloat162float(*reinterpret_cast<const bf16*>(s_h + (f >> 6) * (kBM * 128) + r * 128 + ((((f & 63) >> 3) ^ (r & 7)) << 4) + ((f & 7) << 1)));
+        atomicAdd(p.colsum + (size_t)bb * kD + f, acc);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // closed-form degrees for non-negative features: d_i = xh_i . S_b - xh_i . xh_i,  e_b = sum_i d_i
 //   (relu is the identity on the Gram matrix when every xh >= 0; the diagonal is excluded, utils.py:194-196)
 // ------------------------------------------------------------------------------------------
@@ -1046,7 +1249,21 @@ int run_sweep(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p,
 }
 
 template <int PTPAD>
+int run_prep_tc(const PrepParams& pp, cudaStream_t st) {
+  constexpr size_t smem = prep_tc_smem<PTPAD>();
+  CUtensorMap tm;
+  int rc = imp_make_tmap_2d(&tm, pp.h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kD, pp.row_hi - pp.row_lo, kD * 2, 64, kBM,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  { const int rc_ = imp_ensure_smem((const void*)modularity_prep_tc_kernel<PTPAD>, smem); if (rc_) return rc_; }
+  IMP_LAUNCH("modularity_prep", st, modularity_prep_tc_kernel<PTPAD><<<(pp.row_hi - pp.row_lo + kBM - 1) / kBM, kPtThreads, smem, st>>>(tm, pp));
+  return IMP_OK;
+}
+
+template <int PTPAD>
 int run_prep(const PrepParams& pp, cudaStream_t st) {
+  static const bool ffma = []() { const char* e = getenv("IMP_PREP_FFMA"); return e && atoi(e) != 0; }();   // bring-up switch
+  if (!ffma) return run_prep_tc<PTPAD>(pp, st);
   constexpr size_t smem = prep_smem<PTPAD>();
   { const int rc_ = imp_ensure_smem((const void*)modularity_prep_kernel<PTPAD>, smem); if (rc_) return rc_; }
   IMP_LAUNCH("modularity_prep", st, modularity_prep_kernel<PTPAD><<<(pp.row_hi - pp.row_lo + 63) / 64, 256, smem, st>>>(pp));
