@@ -10,8 +10,9 @@
 // The reference materialises P x N x N and an N^3 matmul; here nothing larger than N x P is stored.
 //
 // Kernels:
-//   prep            : per 64-row tile: inv-norms, xh (bf16, the Gram operand), C = xh . chat (fp32 register-tiled
-//                     FMA) as fixed-point log2 in the tiled layout the sweep streams, column sums of xh, sign flag
+//   prep            : per 128-row tile: inv-norms, xh (bf16, the Gram operand), C = |x|^-1 h . chat^T on tcgen05 (h exact
+//                     in bf16, chat as hi + lo bf16 parts) as fixed-point log2 in the tiled layout the sweep streams,
+//                     column sums of xh, sign flag
 //   degrees_closed  : all features >= 0 (always true behind path_net's ReLU): relu is the identity on the Gram
 //                     matrix, so d_i = xh_i . (sum_j xh_j) - xh_i . xh_i  -- O(N D) instead of an N x N sweep
 //   degrees (Gram)  : general signed features: tcgen05 Gram tiles 128 x 64 (K = 256), relu + row sums
@@ -143,118 +144,6 @@ struct PrepParams {
   int R, B, P1, P2, P1pad;
   int row_lo, row_hi;       // this call covers global rows [row_lo, row_hi) (row_lo % 64 == 0); h points at row row_lo
 };
-constexpr int kXsStride = kD + 4;        // fp32 row stride in smem: 16-byte skew per row (conflict-free float4 reads)
-
-template <int PTPAD>
-constexpr size_t prep_smem() { return (size_t)(64 + PTPAD) * kXsStride * 4; }
-
-template <int PTPAD>
-__global__ void __launch_bounds__(256) modularity_prep_kernel(const PrepParams p) {
-  constexpr int TPG = PTPAD / 8;                  // token slots per thread
-  extern __shared__ float s_prep[];
-  float* xs = s_prep;                             // [64][kXsStride]
-  float* cs = xs + 64 * kXsStride;                // [PTPAD][kXsStride]
-  const int r0 = p.row_lo + blockIdx.x * 64;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // ---------------- phase A ----------------
-  const int data_end0 = __ldg(p.cu + p.B);             // rows past cu[B] belong to no bag
-  bool neg = false;
-#pragma unroll
-  for (int rr = 0; rr < 8; ++rr) {
-    const int rl = warp * 8 + rr, row = r0 + rl;
-    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (row < p.row_hi) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(p.h + (size_t)(row - p.row_lo) * kD + lane * 8);
-      v[0] = bf16lo(raw.x); v[1] = bf16hi(raw.x); v[2] = bf16lo(raw.y); v[3] = bf16hi(raw.y);
-      v[4] = bf16lo(raw.z); v[5] = bf16hi(raw.z); v[6] = bf16lo(raw.w); v[7] = bf16hi(raw.w);
-    }
-    float ss = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { ss += v[k] * v[k]; neg |= (v[k] < 0.f) && (row < data_end0); }
-    ss = warp_sum(ss);
-    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);          // F.normalize eps (utils.py:179,193)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] *= inv;
-    *reinterpret_cast<float4*>(xs + rl * kXsStride + lane * 8) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(xs + rl * kXsStride + lane * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    if (row < p.row_hi) {
-      uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(p.xh + (size_t)row * kD + lane * 8) = o;
-      if (lane == 0) p.invn[row] = inv;
-    }
-  }
-  if (__any_sync(0xffffffffu, neg) && lane == 0) *p.negflag = 1;
-  __syncthreads();
-  // ---------------- phase B ----------------
-  const int tg = threadIdx.x & 7, rg = threadIdx.x >> 3;        // token slots tg*TPG.., rows 2rg, 2rg+1
-  const int Pt = p.P1 + p.P2;
-  const int tile_end = min(r0 + 64, p.row_hi);
-  int b = find_segment(p.cu, p.B, r0);
-  for (; b < p.B; ++b) {
-    const int sa = max(__ldg(p.cu + b), r0), sb = min(__ldg(p.cu + b + 1), tile_end);
-    if (__ldg(p.cu + b) >= tile_end) break;
-    if (sa >= sb) continue;
-    __syncthreads();                                             // cs reuse across bags
-    for (int i = threadIdx.x; i < PTPAD * (kD / 4); i += 256) {
-      const int slot = i / (kD / 4), f4 = i % (kD / 4);
-      int src = -1;
-      if (slot < p.P1) src = slot;
-      else if (slot >= p.P1pad && slot - p.P1pad < p.P2) src = p.P1 + slot - p.P1pad;
-      const float4 c = src >= 0 ? __ldg(reinterpret_cast<const float4*>(p.chat + ((size_t)b * Pt + src) * kD) + f4)
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(cs + slot * kXsStride + f4 * 4) = c;
-    }
-    __syncthreads();
-    // column sums of the bf16-rounded unit rows of this bag (thread = feature)
-    {
-      float acc = 0.f;
-      for (int r = sa; r < sb; ++r) acc += __bfloat162float(__float2bfloat16_rn(xs[(r - r0) * kXsStride + threadIdx.x]));
-      atomicAdd(p.colsum + (size_t)b * kD + threadIdx.x, acc);
-    }
-    float acc0[TPG], acc1[TPG];
-#pragma unroll
-    for (int j = 0; j < TPG; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
-    const float4* x0 = reinterpret_cast<const float4*>(xs + (2 * rg) * kXsStride);
-    const float4* x1 = reinterpret_cast<const float4*>(xs + (2 * rg + 1) * kXsStride);
-    const float4* c4 = reinterpret_cast<const float4*>(cs + (tg * TPG) * kXsStride);
-#pragma unroll 4
-    for (int k4 = 0; k4 < kD / 4; ++k4) {
-      const float4 a = x0[k4], bb = x1[k4];
-#pragma unroll
-      for (int j = 0; j < TPG; ++j) {
-        const float4 c = c4[j * (kXsStride / 4) + k4];
-        acc0[j] = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, acc0[j]))));
-        acc1[j] = fmaf(bb.x, c.x, fmaf(bb.y, c.y, fmaf(bb.z, c.z, fmaf(bb.w, c.w, acc1[j]))));
-      }
-    }
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int row = r0 + 2 * rg + rr;
-      if (row < sa || row >= sb) continue;
-#pragma unroll
-      for (int j = 0; j < TPG; ++j) {
-        const int slot = tg * TPG + j;
-        const float dot = rr ? acc1[j] : acc0[j];
-        int fix = kNMax;                                          // padding slots have zero tokens: dot == 0
-        if (dot > 0.f) fix = min(kNMax, max(0, __float2int_rn(((float)kCOff - log2f(dot)) * (float)(1 << kLogShift))));
-        // low 5 bits: token index inside its group (column-side operand); the row side masks them off
-        p.lfix[lfix_index(row, slot, PTPAD)] = (float)(fix * 32 + (slot < p.P1pad ? slot : slot - p.P1pad));
-      }
-    }
-  }
-  // rows of the tile that belong to no bag (past cu[B]: tile padding, or the unused tail of a buffer sized for the
-  // worst case) are masked in the sweep, but its loads must stay finite: 0 * NaN would poison the sums
-  const int data_end = __ldg(p.cu + p.B);
-  if (r0 + 64 > data_end) {
-    for (int i = threadIdx.x; i < PTPAD * 64; i += 256) {
-      const int slot = i >> 6, rl = i & 63;
-      if (r0 + rl >= data_end) p.lfix[lfix_index(r0 + rl, slot, PTPAD)] = (float)(kNMax * 32);
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // prep on tcgen05.  C = |x|^-1 (h . chat^T): h is EXACT in bf16 (it is stored that way), so with chat split into
 // hi + lo bf16 parts (chat - hi - lo ~ 2^-17 chat) the tensor core delivers the inner products to ~4e-6 relative --
@@ -1261,14 +1150,7 @@ int run_prep_tc(const PrepParams& pp, cudaStream_t st) {
 }
 
 template <int PTPAD>
-int run_prep(const PrepParams& pp, cudaStream_t st) {
-  static const bool ffma = []() { const char* e = getenv("IMP_PREP_FFMA"); return e && atoi(e) != 0; }();   // bring-up switch
-  if (!ffma) return run_prep_tc<PTPAD>(pp, st);
-  constexpr size_t smem = prep_smem<PTPAD>();
-  { const int rc_ = imp_ensure_smem((const void*)modularity_prep_kernel<PTPAD>, smem); if (rc_) return rc_; }
-  IMP_LAUNCH("modularity_prep", st, modularity_prep_kernel<PTPAD><<<(pp.row_hi - pp.row_lo + 63) / 64, 256, smem, st>>>(pp));
-  return IMP_OK;
-}
+int run_prep(const PrepParams& pp, cudaStream_t st) { return run_prep_tc<PTPAD>(pp, st); }
 
 struct Carve {
   bf16* xh; float* invn; float* lfix; float* d; float* T; double* e; double* s; float* colsum; int* negflag;
