@@ -1,6 +1,7 @@
 """Turn ncu outputs brought back in gpurun_out/ into the compact summaries committed here.
   python profiles/summarize.py launches gpurun_out/launches.csv  > profiles/rNN_launches.md
   python profiles/summarize.py full gpurun_out/prof.ncu-rep      > profiles/rNN_ncu_full.md
+  python profiles/summarize.py traffic gpurun_out/prof.ncu-rep 32 "<what was captured>" > profiles/ncu_traffic.json
 """
 import csv
 import subprocess
@@ -46,6 +47,34 @@ def launches(path):
     print("\ntotal over captured launches: %.1f %s (cold-cache, serialised: compare shares)" % (tot, unit))
 
 
+NAME_MAP = [("pathnet_fwd_kernel", "pathnet_fwd"), ("pathnet_dw_kernel", "pathnet_dw"), ("pool_bwd_dz_kernel", "pool_bwd_dz"),
+            ("pool_tc_kernel<32, 0>", "pool_fwd"), ("pool_tc_kernel<64, 0>", "pool_fwd"),
+            ("pool_tc_kernel<32, 1>", "pool_bwd_dq"), ("pool_tc_kernel<64, 1>", "pool_bwd_dq"),
+            ("modularity_sweep_kernel", "modularity_sweep"), ("modularity_prep_tc_kernel", "modularity_prep"),
+            ("modularity_degrees_closed_kernel", "modularity_degrees_closed"), ("modularity_finish_tc_kernel", "modularity_finish")]
+
+
+def traffic(path, bags, source):
+    """profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, keyed by the launch names
+    bench.py uses (mean over the captured launches of a kernel)."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = {}
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]]
+        key = next((v for k, v in NAME_MAP if k in name), None)
+        if key is None:
+            continue
+        b = sum(float(r[idx[m]].replace(",", "")) * scale[units[idx[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        acc.setdefault(key, []).append(b)
+    print(json.dumps({"bags_per_step": int(bags), "source": source,
+                      "bytes_per_launch": {k: sum(v) / len(v) for k, v in sorted(acc.items())}}, indent=1))
+
+
 def full(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -61,4 +90,7 @@ def full(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
