@@ -23,8 +23,10 @@ for lens, P, shared in (([1], 6, False), ([37, 129, 300], 32, True), ([1000, 64]
         dq2, dz = kernels.pool_bwd(h, cu, max(lens), [qt, qt], [dp, dp], [lse, lse], [delta, delta], 0, want_dz=True, db1=db1)
     c1 = torch.randn(len(lens), min(P, 32), 256, device=dev)
     c2 = torch.randn(len(lens), 7, 256, device=dev)
-    t = MOD.modularity_terms(h, cu, max(lens), c1, c2)
+    # a one-patch bag has an empty graph (e = 0): the loss is 0/0 here exactly as in the reference (utils.py:201,222)
+    t = MOD.modularity_terms(h, cu, max(lens), c1, c2) if min(lens) > 1 else torch.zeros(1, device=dev)
     torch.cuda.synchronize()
+    print(lens, P, shared, 'pooled', bool(torch.isfinite(pooled).all()), 'lse', bool(torch.isfinite(lse).all()), 'dq', bool(torch.isfinite(dq).all()), 'terms', bool(torch.isfinite(t).all()), (bool(torch.isfinite(dq2).all()), bool(torch.isfinite(dz.float()).all()), bool(torch.isfinite(db1).all())) if P <= 32 else None, flush=True)
     assert torch.isfinite(pooled).all() and torch.isfinite(dq).all() and torch.isfinite(t).all()
 # the whole hot path from the reference batch layout (worst-case sized packed buffer: rows past cu[B] belong to no bag)
 net = M.IMPHotPath(n_proto=6, dropout=0.25, seed=0).to(dev)
