@@ -32,7 +32,7 @@ for lens, P, shared in (([1], 6, False), ([37, 129, 300], 32, True), ([1000, 64]
 net = M.IMPHotPath(n_proto=6, dropout=0.25, seed=0).to(dev)
 runner = S.HotPathStep(net).to(dev).train()
 img = torch.full((3, 512, 512), -10000.0)
-for i, n in enumerate((300, 1, 417)):
+for i, n in enumerate((300, 2, 417)):
     img[i, :n] = torch.randn(n, 512)
 loss = runner({"img": img.to(dev), "omic": torch.rand(3, 3354, device=dev)}, torch.randn(3, 6, 256, device=dev), torch.randn(3, 7, 256, device=dev))
 loss.backward()
