@@ -103,9 +103,10 @@ def test_rounding_point_attribution():
 
 
 def _modularity_case(n, p, q, seed, chunk):
-    """Loss and token gradient of both token groups at full size.  Gradient bounds against the full-precision
-    oracle: 1e-3 at 16 384 patches, 3e-3 at 120 000 (the per-row 32-bit fixed-point accumulators of T share their
-    range between more columns; profiles/r02_parity.md)."""
+    """Loss and token gradient of both token groups at full size, held to the north-star 1e-3 against the
+    full-precision oracle at 16 384 and at 120 000 patches (a sweep CTA covers at most 16 384 columns, so the 32-bit
+    fixed-point accumulators of T keep the same resolution on giant bags; before that cap the 120 000-patch gradient
+    sat at 2.1e-3; profiles/r02_parity.md)."""
     from imp_b200 import modularity as M
     from oracle import imp_oracle as O
     L = Ledger("modularity[N=%d,P=%d+%d]" % (n, p, q))
@@ -119,7 +120,7 @@ def _modularity_case(n, p, q, seed, chunk):
     (loss[0, 0] + loss[0, 1]).backward()
     torch.cuda.synchronize()
     h64 = h.double()
-    gtol = 1e-3 if n <= 16384 else 3e-3
+    gtol = 1e-3
     for tag, cd, cref, li in (("proto", c1d, c[0].double(), 0), ("omic", c2d, c2[0].double(), 1)):
         for gram_bf16, who in ((False, "oracle fp64"), (True, "oracle fp64, bf16 Gram operand")):
             ref, dref = O.modularity(cref, h64, chunk=chunk, gram_bf16=gram_bf16)
