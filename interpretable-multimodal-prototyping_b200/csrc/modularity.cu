@@ -1282,7 +1282,8 @@ int launch_modularity_execute(const bf16* h_local, int local_rows, int row_lo, i
     int nsplit = std::max(1, std::min((2 * imp_num_sms() + row_blocks * B - 1) / (row_blocks * B), std::max(1, col_tiles / 16)));
     // a CTA accumulates T_i over its own columns in 32-bit fixed point whose scale is set by the column count: at most
     // 16 384 columns (256 tiles) per CTA keeps the resolution of a 120 000-patch bag at that of a 16 384-patch one
-    nsplit = std::max(nsplit, (col_tiles + 255) / 256);
+    static const int max_tiles = []() { const char* e = getenv("IMP_SWEEP_MAXTILES"); return e && atoi(e) > 0 ? atoi(e) : 256; }();
+    nsplit = std::max(nsplit, (col_tiles + max_tiles - 1) / max_tiles);
     gp.tiles_per_split = (col_tiles + nsplit - 1) / nsplit;
     nsplit = (col_tiles + gp.tiles_per_split - 1) / gp.tiles_per_split;
     const dim3 grid(row_blocks, nsplit, B);
