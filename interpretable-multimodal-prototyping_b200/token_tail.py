@@ -68,18 +68,13 @@ def nystrom_short(q, k, v, m: int, iters: int):
     cs = torch.maximum((p / m + cvec.sum(-2)).max(), (p / m + dmat.sum(-2)).max())
     top = torch.cat([s.new_full(s.shape[:-2] + (1, 1), p / m), s.new_full(s.shape[:-2] + (1, n), rp / m)], dim=-1)
     mat = torch.cat([top, torch.cat([rp * cvec, dmat], dim=-1)], dim=-2)          # M(A), (B,H,n+1,n+1)
-    lead = mat.shape[:-2]
-    mat = mat.reshape(-1, n + 1, n + 1)
-    eye = torch.eye(n + 1, device=s.device, dtype=s.dtype).expand_as(mat)
+    eye = torch.eye(n + 1, device=s.device, dtype=s.dtype)
     z = mat.transpose(-1, -2) / (rs * cs)
-    for _ in range(iters):                                       # z <- 0.25 z (13 I - az (15 I - az (7 I - az))), five kernels
-        az = torch.bmm(mat, z)
-        t = torch.baddbmm(eye, az, 7.0 * eye - az, beta=15.0, alpha=-1.0)
-        t = torch.baddbmm(eye, az, t, beta=3.25, alpha=-0.25)
-        z = torch.bmm(z, t)
-    v1 = F.pad(v, (0, 0, 1, 0)).reshape(-1, n + 1, v.shape[-1])  # coordinates of [0; v]: zero along u
-    out = torch.bmm(mat, torch.bmm(z, torch.bmm(mat, v1)))
-    return out.reshape(lead + out.shape[-2:])[..., 1:, :]
+    for _ in range(iters):
+        az = mat @ z
+        z = 0.25 * z @ (13 * eye - az @ (15 * eye - az @ (7 * eye - az)))
+    v1 = F.pad(v, (0, 0, 1, 0))                                  # coordinates of [0; v]: zero along u
+    return (mat @ (z @ (mat @ v1)))[..., 1:, :]
 
 
 class NystromAttention(nn.Module):
