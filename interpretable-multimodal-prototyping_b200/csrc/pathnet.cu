@@ -119,22 +119,32 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       const int row = tile * kBM + quarter * 32 + lane;
       const bool row_ok = row < p.rows;
       bf16* out_row = p.h + (size_t)row * kD;
-#pragma unroll 1
+      // two 32-column chunks in flight: the TMEM load of the next chunk is issued before the current one is processed
+      // (with one chunk at a time the ~300-cycle tcgen05.ld latency was exposed four times per tile and the epilogue,
+      // not the tensor pipe, set the tile time)
+      uint32_t vbuf[2][32];
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kD + half * 128;
+      tmem_ld32(tbase, vbuf[0]);
+#pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         const int col0 = half * 128 + cc * 32;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kD + col0, v);
         tmem_ld_wait();
+        if (cc + 1 < 4) tmem_ld32(tbase + (cc + 1) * 32, vbuf[(cc + 1) & 1]);
+        const uint32_t (&v)[32] = vbuf[cc & 1];
         uint32_t packed[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          float f[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) f[e] = fmaxf(__uint_as_float(v[j + e]) + s_bias[col0 + j + e], 0.f);
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + col0 + j);
+          float f[4] = {fmaxf(__uint_as_float(v[j]) + bb.x, 0.f), fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f),
+                        fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.f)};
           if (p.drop_thresh) {
-            // 16 hash bits per element (p is quantised to 1/65536): two mixed words per group of four columns
-            const uint32_t h0 = mix32(seed ^ ((uint32_t)row * 64u + (uint32_t)((col0 + j) >> 2)) * 0x9E3779B1u);
-            const uint32_t h1 = mix32(h0 + 0x6a09e667u);
+            // 16 hash bits per element (p is quantised to 1/65536): one 32-bit mix and one 32x32->64 multiply per four columns
+            uint32_t z = (seed ^ ((uint32_t)row * 64u + (uint32_t)((col0 + j) >> 2))) * 0x9E3779B1u;
+            z ^= z >> 15;
+            z *= 0x85ebca6bu;
+            z ^= z >> 13;
+            const unsigned long long w = (unsigned long long)z * 0xD6E8FEB86659FD93ull;
+            const uint32_t h0 = (uint32_t)w ^ (uint32_t)(w >> 32), h1 = (uint32_t)(w >> 29);
             const uint32_t bits[4] = {h0 & 0xffffu, h0 >> 16, h1 & 0xffffu, h1 >> 16};
 #pragma unroll
             for (int e = 0; e < 4; ++e)
