@@ -6,12 +6,6 @@
 // Both are warp-specialised persistent kernels: one TMA producer warp, one MMA-issuer warp
 // (a single thread issues tcgen05.mma, accumulators live in TMEM) and epilogue warps that read
 // TMEM with tcgen05.ld.  Operands are staged in shared memory by TMA with the 128-byte swizzle.
-//
-// The forward runs as CLUSTERS OF TWO CTAs that share the W1 stream: every k-stage needs the same 256 x 64 slab of W1
-// in both CTAs, so each CTA loads one 128-row half and TMA-multicasts it into both shared memories.  Without it each
-// 128-row tile pulls 256 KB of W1 through L2 next to its 128 KB of x and 64 KB of h: 148 SMs x 448 KB per 6 us = 11 TB/s,
-// the L2 ceiling of the chip (~6300 B/clk), not HBM, set the tile time.  A stage is refilled only when BOTH CTAs have
-// released it: the MMA issuer's commit arrives on the empty barrier of both CTAs (count 2).
 #include "common.cuh"
 
 namespace {
@@ -39,7 +33,7 @@ struct FwdParams {
   const uint32_t* seed_offset;   // device word XOR-ed into the seed, or null
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -56,23 +50,18 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = p.kdim / kBK;
   const uint32_t seed = p.seed ^ (p.seed_offset ? __ldg(p.seed_offset) : 0u);
-  const uint32_t cta_rank = cluster_ctarank();
-  // both CTAs of a cluster step through the same number of k-stages: tiles past the end are dummies (TMA zero-fills
-  // rows outside the tensor, the epilogue stores nothing)
-  const int iters = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (threadIdx.x < 256) s_bias[threadIdx.x] = p.bias[threadIdx.x];
   if (warp == kEpiWarps && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }     // empty: this CTA's and the peer's commit
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
     mbar_fence_init();
   }
   if (warp == kEpiWarps + 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();                       // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -80,15 +69,13 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        const int tile = it * (int)gridDim.x + (int)blockIdx.x;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);                       // released by both CTAs
-          mbar_arrive_expect_tx(&full[stage], kStageBytes);         // x box + both halves of the W1 slab
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], kStageBytes);
           uint8_t* sa = stage_base + (size_t)stage * kStageBytes;
           tma_load_2d(sa, &tm_x, &full[stage], kb * kBK, tile * kBM);
-          tma_load_2d_mc(sa + kStageBytesA + cta_rank * (kStageBytesB / 2), &tm_w, &full[stage], kb * kBK, (int)cta_rank * (kD / 2),
-                         (uint16_t)0x3);
+          tma_load_2d(sa + kStageBytesA, &tm_w, &full[stage], kb * kBK, 0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -97,8 +84,8 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, kD, 0, 0);
-      int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -114,7 +101,7 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             uint64_t bd = umma_desc_sw128(sb + k * 32, 0, 1024);
             umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
           }
-          umma_commit_mc(&empty[stage], (uint16_t)0x3);             // this stage is free here: tell both producers
+          umma_commit(&empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);
@@ -124,8 +111,8 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     // ------------------------------ epilogue: TMEM -> bias/relu/dropout -> bf16 -> HBM ----
     const int quarter = warp & 3;         // TMEM lane quarter this warp may access
     const int half = warp >> 2;           // which 128 of the 256 output columns
-    for (int it = 0; it < iters; ++it) {
-      const int tile = it * (int)gridDim.x + (int)blockIdx.x;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
@@ -180,7 +167,6 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();                       // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == kEpiWarps + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -339,8 +325,8 @@ int launch_pathnet_fwd(const bf16* x, const bf16* w1, const float* b1, bf16* h, 
   int rc;
   if ((rc = imp_make_tmap_2d(&tm_x, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kdim, rows, (uint64_t)kdim * 2, kBK, kBM,
                              CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = imp_make_tmap_2d(&tm_w, w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kdim, kD, (uint64_t)kdim * 2, kBK, kD / 2,
-                             CU_TENSOR_MAP_SWIZZLE_128B))) return rc;      // one 128-row half of a W1 slab per CTA of the pair
+  if ((rc = imp_make_tmap_2d(&tm_w, w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kdim, kD, (uint64_t)kdim * 2, kBK, kD,
+                             CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   FwdParams p;
   p.bias = b1; p.h = h; p.rows = rows; p.kdim = kdim;
   p.num_tiles = (rows + kBM - 1) / kBM;
@@ -350,7 +336,6 @@ int launch_pathnet_fwd(const bf16* x, const bf16* w1, const float* b1, bf16* h, 
   p.seed_offset = imp_seed_offset_ptr();
   { const int rc_ = imp_ensure_smem((const void*)pathnet_fwd_kernel, kFwdSmem); if (rc_) return rc_; }
   int grid = min(p.num_tiles, imp_num_sms());
-  grid = (grid + 1) & ~1;                   // clusters of two CTAs
   IMP_LAUNCH("pathnet_fwd", st, pathnet_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(tm_x, tm_w, p));
   return IMP_OK;
 }
