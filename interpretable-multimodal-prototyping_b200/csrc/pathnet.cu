@@ -13,13 +13,18 @@ namespace {
 constexpr int kD = 256;        // hidden dim (MODEL.HIDDEN_DIM)
 constexpr int kBM = 128;       // patch rows per tile
 constexpr int kBK = 64;        // K elements per stage (one 128 B swizzle row of bf16)
-constexpr int kStages = 4;
+// Two rings with different depths.  x comes from HBM (~2 us under load): 8 stages x 16 KB = 128 KB in flight per SM, above
+// the ~90 KB that 44 GB/s per SM x latency needs (a common 4-stage ring kept only 64 KB of x in flight and capped the
+// kernel at 4.6 TB/s).  The W1 slabs every tile re-reads are L2 hits with a fraction of that latency: 2 stages x 32 KB.
+// (Sharing the W1 stream between a CTA pair by TMA multicast was built and measured: no gain, L2 already serves
+// concurrent requests for the same lines once.)
+constexpr int kXStages = 8;
+constexpr int kWStages = 2;
 constexpr int kEpiWarps = 8;
 constexpr int kFwdThreads = (kEpiWarps + 2) * 32;
 constexpr uint32_t kStageBytesA = kBM * kBK * 2;     // 16 KB
 constexpr uint32_t kStageBytesB = kD * kBK * 2;      // 32 KB
-constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
-constexpr size_t kFwdSmem = 1024 + (size_t)kStages * kStageBytes + 256 * 4 + 256;
+constexpr size_t kFwdSmem = 1024 + (size_t)kXStages * kStageBytesA + (size_t)kWStages * kStageBytesB + 256 * 4 + 256;
 
 struct FwdParams {
   const float* bias;      // (256)
@@ -38,13 +43,16 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                    const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* stage_base = smem;
-  float* s_bias = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes);
+  uint8_t* x_base = smem;
+  uint8_t* w_base = smem + (size_t)kXStages * kStageBytesA;
+  float* s_bias = reinterpret_cast<float*>(w_base + (size_t)kWStages * kStageBytesB);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
-  uint64_t* full = bars;                  // [kStages]
-  uint64_t* empty = bars + kStages;       // [kStages]
-  uint64_t* tfull = bars + 2 * kStages;   // [2]
-  uint64_t* tempty = tfull + 2;           // [2]
+  uint64_t* xfull = bars;                          // [kXStages]
+  uint64_t* xempty = xfull + kXStages;             // [kXStages]
+  uint64_t* wfull = xempty + kXStages;             // [kWStages]
+  uint64_t* wempty = wfull + kWStages;             // [kWStages]
+  uint64_t* tfull = wempty + kWStages;             // [2]
+  uint64_t* tempty = tfull + 2;                    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -55,7 +63,8 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   if (warp == kEpiWarps && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kXStages; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
+    for (int i = 0; i < kWStages; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
     mbar_fence_init();
   }
@@ -68,41 +77,56 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   if (warp == kEpiWarps) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], kStageBytes);
-          uint8_t* sa = stage_base + (size_t)stage * kStageBytes;
-          tma_load_2d(sa, &tm_x, &full[stage], kb * kBK, tile * kBM);
-          tma_load_2d(sa + kStageBytesA, &tm_w, &full[stage], kb * kBK, 0);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+      // x runs up to kXStages k-blocks ahead of the MMAs, W1 only kWStages: the two loads of a k-block are issued
+      // when THEIR ring has room, x first (the long-latency one)
+      const int total = ((p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * kblocks;
+      int xi = 0, wi = 0;                                  // next k-block (flattened over this CTA's tiles) per ring
+      while (wi < total) {
+        while (xi < total) {
+          const int xs = xi % kXStages;
+          if (!mbar_test(&xempty[xs], ((xi / kXStages) & 1) ^ 1)) break;
+          const int tile = (int)blockIdx.x + (xi / kblocks) * (int)gridDim.x, kb = xi % kblocks;
+          mbar_arrive_expect_tx(&xfull[xs], kStageBytesA);
+          tma_load_2d(x_base + (size_t)xs * kStageBytesA, &tm_x, &xfull[xs], kb * kBK, tile * kBM);
+          ++xi;
         }
+        {
+          const int ws = wi % kWStages;
+          if (mbar_test(&wempty[ws], ((wi / kWStages) & 1) ^ 1)) {
+            mbar_arrive_expect_tx(&wfull[ws], kStageBytesB);
+            tma_load_2d(w_base + (size_t)ws * kStageBytesB, &tm_w, &wfull[ws], (wi % kblocks) * kBK, 0);
+            ++wi;
+            continue;
+          }
+        }
+        __nanosleep(20);
       }
     }
   } else if (warp == kEpiWarps + 1) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, kD, 0, 0);
-      int stage = 0; uint32_t phase = 0; int it = 0;
+      int it = 0, n = 0;                                   // n: k-blocks issued so far (both rings advance together)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kD;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full[stage], phase);
+        for (int kb = 0; kb < kblocks; ++kb, ++n) {
+          const int xs = n % kXStages, ws = n % kWStages;
+          mbar_wait(&xfull[xs], (n / kXStages) & 1);
+          mbar_wait(&wfull[ws], (n / kWStages) & 1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + (size_t)stage * kStageBytes);
-          const uint32_t sb = sa + kStageBytesA;
+          const uint32_t sa = smem_u32(x_base + (size_t)xs * kStageBytesA);
+          const uint32_t sb = smem_u32(w_base + (size_t)ws * kStageBytesB);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             uint64_t ad = umma_desc_sw128(sa + k * 32, 0, 1024);
             uint64_t bd = umma_desc_sw128(sb + k * 32, 0, 1024);
             umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          umma_commit(&xempty[xs]);
+          umma_commit(&wempty[ws]);
         }
         umma_commit(&tfull[acc]);
       }
