@@ -7,24 +7,27 @@
 // (a single thread issues tcgen05.mma, accumulators live in TMEM) and epilogue warps that read
 // TMEM with tcgen05.ld.  Operands are staged in shared memory by TMA with the 128-byte swizzle.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
 constexpr int kD = 256;        // hidden dim (MODEL.HIDDEN_DIM)
 constexpr int kBM = 128;       // patch rows per tile
 constexpr int kBK = 64;        // K elements per stage (one 128 B swizzle row of bf16)
-// Two rings with different depths.  x comes from HBM (~2 us under load): 8 stages x 16 KB = 128 KB in flight per SM, above
-// the ~90 KB that 44 GB/s per SM x latency needs (a common 4-stage ring kept only 64 KB of x in flight and capped the
-// kernel at 4.6 TB/s).  The W1 slabs every tile re-reads are L2 hits with a fraction of that latency: 2 stages x 32 KB.
-// (Sharing the W1 stream between a CTA pair by TMA multicast was built and measured: no gain, L2 already serves
-// concurrent requests for the same lines once.)
-constexpr int kXStages = 8;
-constexpr int kWStages = 2;
-constexpr int kEpiWarps = 8;
+// Separate rings for x (HBM) and the W1 slabs every tile re-reads (L2 hits), depths as template parameters.  Measured on
+// 32 bags x 16 384 patches (ms): (x,W) = (4,4) 0.169 | (5,3) 0.167 | (6,3) 0.172 | (8,2) 0.188.  Variants that were built,
+// measured and dropped: W1 stage multicast to a CTA pair 0.165; 16 epilogue warps 0.184; h tile
+// through shared memory + TMA store 0.186; one half of W1 resident in shared memory (x-only ring of 5 stages) 0.184.
+// Ablation of this kernel: loads only 0.123, + MMAs 0.142, + epilogue 0.145, all 0.169-0.180: the ring (192 KB in
+// flight per SM) cannot hide the load latency once slots are also held for the MMAs.
+constexpr int kEpiWarps = 8;       // two per TMEM lane quarter, 128 output columns each
+constexpr int kColsPerWarp = kD / (kEpiWarps / 4);
+constexpr int kChunks = kColsPerWarp / 32;
 constexpr int kFwdThreads = (kEpiWarps + 2) * 32;
 constexpr uint32_t kStageBytesA = kBM * kBK * 2;     // 16 KB
 constexpr uint32_t kStageBytesB = kD * kBK * 2;      // 32 KB
-constexpr size_t kFwdSmem = 1024 + (size_t)kXStages * kStageBytesA + (size_t)kWStages * kStageBytesB + 256 * 4 + 256;
+template <int kXStages, int kWStages>
+constexpr size_t fwd_smem() { return 1024 + (size_t)kXStages * kStageBytesA + (size_t)kWStages * kStageBytesB + 256 * 4 + 256; }
 
 struct FwdParams {
   const float* bias;      // (256)
@@ -38,6 +41,7 @@ struct FwdParams {
   const uint32_t* seed_offset;   // device word XOR-ed into the seed, or null
 };
 
+template <int kXStages, int kWStages>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const FwdParams p) {
@@ -81,7 +85,7 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       // when THEIR ring has room, x first (the long-latency one)
       const int total = ((p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * kblocks;
       int xi = 0, wi = 0;                                  // next k-block (flattened over this CTA's tiles) per ring
-      while (wi < total) {
+      while (wi < total || xi < total) {                    // either ring may be the one that still owes loads
         while (xi < total) {
           const int xs = xi % kXStages;
           if (!mbar_test(&xempty[xs], ((xi / kXStages) & 1) ^ 1)) break;
@@ -90,7 +94,7 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           tma_load_2d(x_base + (size_t)xs * kStageBytesA, &tm_x, &xfull[xs], kb * kBK, tile * kBM);
           ++xi;
         }
-        {
+        if (wi < total) {
           const int ws = wi % kWStages;
           if (mbar_test(&wempty[ws], ((wi / kWStages) & 1) ^ 1)) {
             mbar_arrive_expect_tx(&wfull[ws], kStageBytesB);
@@ -134,7 +138,7 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   } else {
     // ------------------------------ epilogue: TMEM -> bias/relu/dropout -> bf16 -> HBM ----
     const int quarter = warp & 3;         // TMEM lane quarter this warp may access
-    const int half = warp >> 2;           // which 128 of the 256 output columns
+    const int half = warp >> 2;           // which kColsPerWarp of the 256 output columns
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -147,13 +151,13 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       // (with one chunk at a time the ~300-cycle tcgen05.ld latency was exposed four times per tile and the epilogue,
       // not the tensor pipe, set the tile time)
       uint32_t vbuf[2][32];
-      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kD + half * 128;
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kD + half * kColsPerWarp;
       tmem_ld32(tbase, vbuf[0]);
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int col0 = half * 128 + cc * 32;
+      for (int cc = 0; cc < kChunks; ++cc) {
+        const int col0 = half * kColsPerWarp + cc * 32;
         tmem_ld_wait();
-        if (cc + 1 < 4) tmem_ld32(tbase + (cc + 1) * 32, vbuf[(cc + 1) & 1]);
+        if (cc + 1 < kChunks) tmem_ld32(tbase + (cc + 1) * 32, vbuf[(cc + 1) & 1]);
         const uint32_t (&v)[32] = vbuf[cc & 1];
         uint32_t packed[16];
 #pragma unroll
@@ -358,9 +362,23 @@ int launch_pathnet_fwd(const bf16* x, const bf16* w1, const float* b1, bf16* h, 
   p.keep_scale = p.drop_thresh ? 65536.f / (65536.f - (float)p.drop_thresh) : 1.f;
   p.seed = seed;
   p.seed_offset = imp_seed_offset_ptr();
-  { const int rc_ = imp_ensure_smem((const void*)pathnet_fwd_kernel, kFwdSmem); if (rc_) return rc_; }
   int grid = min(p.num_tiles, imp_num_sms());
-  IMP_LAUNCH("pathnet_fwd", st, pathnet_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(tm_x, tm_w, p));
+  static const int cfg = []() { const char* e = getenv("IMP_PATHNET_RINGS"); return e ? atoi(e) : 0; }();   // tuning switch
+#define IMP_PF(XS, WS)                                                                                               \
+  do {                                                                                                               \
+    constexpr size_t smem = fwd_smem<XS, WS>();                                                                      \
+    static_assert(smem <= 227 * 1024, "pathnet_fwd shared memory");                                                  \
+    { const int rc_ = imp_ensure_smem((const void*)pathnet_fwd_kernel<XS, WS>, smem); if (rc_) return rc_; }         \
+    IMP_LAUNCH("pathnet_fwd", st, pathnet_fwd_kernel<XS, WS><<<grid, kFwdThreads, smem, st>>>(tm_x, tm_w, p));      \
+  } while (0)
+  switch (cfg) {
+    case 1: IMP_PF(8, 2); break;
+    case 2: IMP_PF(6, 3); break;
+    case 3: IMP_PF(5, 3); break;
+    case 4: IMP_PF(3, 4); break;
+    default: IMP_PF(4, 4); break;
+  }
+#undef IMP_PF
   return IMP_OK;
 }
 

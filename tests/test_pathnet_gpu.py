@@ -9,20 +9,38 @@ def _ref_fwd(x, w, b):
     return torch.relu(x.float() @ w.float().t() + b)
 
 
-@pytest.mark.parametrize("rows", [128, 1, 77, 1000, 4096 + 33])
+@pytest.mark.parametrize("rows", [128, 1, 77, 1000, 4096 + 33, 148 * 128 * 5 + 57])
 def test_pathnet_fwd(rows):
     from imp_b200 import _lib
     g = torch.Generator(device="cuda").manual_seed(rows)
     x = torch.randn(rows, 512, device="cuda", generator=g).bfloat16()
     w = (torch.randn(256, 512, device="cuda", generator=g) * 0.05).bfloat16()
     b = torch.randn(256, device="cuda", generator=g) * 0.1
-    h = torch.empty(rows, 256, device="cuda", dtype=torch.bfloat16)
+    guard = torch.full((rows + 128, 256), 7.0, device="cuda", dtype=torch.bfloat16)   # rows past the end stay untouched
+    h = guard[:rows]
     _lib.call("imp_pathnet_fwd", x, w, b, h, rows, 512, 0.0, 0, _lib.stream_ptr())
     torch.cuda.synchronize()
+    assert bool((guard[rows:] == 7.0).all())
     ref = _ref_fwd(x, w, b)
     err = (h.float() - ref).abs().max().item()
     assert err <= 2e-2 * ref.abs().max().item() + 1e-3, err      # bf16 output rounding
     # tighter: relative Frobenius error
+    assert ((h.float() - ref).norm() / ref.norm()).item() < 5e-3
+
+
+@pytest.mark.parametrize("kdim", [256, 1024])
+def test_pathnet_fwd_streaming_variant(kdim):
+    """kdim != 512 takes the kernel that streams W1 per tile (the W1-stationary one holds exactly 128 x 512)."""
+    from imp_b200 import _lib
+    rows = 148 * 128 * 3 + 5
+    g = torch.Generator(device="cuda").manual_seed(kdim)
+    x = torch.randn(rows, kdim, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(256, kdim, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(256, device="cuda", generator=g) * 0.1
+    h = torch.empty(rows, 256, device="cuda", dtype=torch.bfloat16)
+    _lib.call("imp_pathnet_fwd", x, w, b, h, rows, kdim, 0.0, 0, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    ref = _ref_fwd(x, w, b)
     assert ((h.float() - ref).norm() / ref.norm()).item() < 5e-3
 
 
