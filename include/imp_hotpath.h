@@ -101,6 +101,10 @@ int imp_cast_bf16(const float* src, void* dst, size_t n, void* stream);
  * loss (n_bags,2) fp32 <- -100 tr((W/e) delta) per group (utils.py:222-228; 0 for an empty group);
  * dchat (n_bags, n_tok1+n_tok2, 256) fp32 <- d loss_group / d chat. */
 size_t imp_modularity_workspace_bytes(int total_rows, int n_bags, int n_tok1, int n_tok2);
+/* Host-only query (no launch): the column split the pair sweep uses for bags of at most max_len patches of which this
+ * call owns runs of at most own_rows rows (own_rows = max_len unless the bag is sharded): grid = (ceil(own_rows/128),
+ * *nsplit, n_bags) CTAs of *tiles_per_split 64-column tiles each. */
+int imp_modularity_sweep_plan(int own_rows, int max_len, int n_bags, int* nsplit, int* tiles_per_split);
 int imp_modularity(const void* h, int total_rows, const int* cu_seqlens, int n_bags, int max_len,
                    const float* chat, int n_tok1, int n_tok2, float temp, void* workspace, float* loss,
                    float* dchat, void* stream);

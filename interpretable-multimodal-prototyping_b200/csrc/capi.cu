@@ -225,6 +225,12 @@ extern "C" int imp_cast_bf16(const float* src, void* dst, size_t n, void* stream
 extern "C" size_t imp_modularity_workspace_bytes(int total_rows, int n_bags, int n_tok1, int n_tok2) {
   return modularity_workspace_bytes(total_rows, n_bags, n_tok1, n_tok2);
 }
+extern "C" int imp_modularity_sweep_plan(int own_rows, int max_len, int n_bags, int* nsplit, int* tiles_per_split) {
+  if (!nsplit || !tiles_per_split) IMP_FAIL(IMP_ERR_ARG, "imp_modularity_sweep_plan: null pointer");
+  if (own_rows <= 0 || max_len <= 0 || n_bags <= 0) IMP_FAIL(IMP_ERR_ARG, "imp_modularity_sweep_plan: sizes must be positive");
+  modularity_sweep_plan(own_rows, max_len, n_bags, nsplit, tiles_per_split);
+  return IMP_OK;
+}
 extern "C" int imp_modularity(const void* h, int total_rows, const int* cu_seqlens, int n_bags, int max_len,
                               const float* chat, int n_tok1, int n_tok2, float temp, void* workspace, float* loss,
                               float* dchat, void* stream) {

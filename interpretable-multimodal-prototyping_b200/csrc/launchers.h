@@ -28,6 +28,7 @@ int launch_cast_bf16(const float* src, bf16* dst, size_t n, cudaStream_t st);
 
 // modularity.cu
 size_t modularity_workspace_bytes(int total_rows, int B, int P1, int P2);
+void modularity_sweep_plan(int own_len, int max_len, int B, int* nsplit, int* tiles_per_split);
 int launch_modularity(const bf16* h, int total_rows, const int* cu, int B, int max_len, const float* chat, int P1, int P2,
                       float temp, void* workspace, float* loss, float* dchat, cudaStream_t st);
 void modularity_workspace_sections(int total_rows, int B, int P1, int P2, size_t* offsets, size_t* sizes);

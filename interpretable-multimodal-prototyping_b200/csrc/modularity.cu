@@ -1119,6 +1119,40 @@ modularity_finish_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const Fini
   }
 }
 
+}  // namespace
+
+// Column split of the pair sweep: grid = (row blocks of 128, nsplit, bags), a CTA covers tiles_per_split 64-column tiles.
+//  - at least 16 column tiles per CTA (the A block load, the row operand and the flush are per CTA: ~0.5 tile);
+//  - at most `max_tiles` (256 = 16 384 columns): a CTA accumulates T_i over its own columns in 32-bit fixed point whose
+//    scale is set by the column count, which keeps the resolution of a 120 000-patch bag at that of a 16 384-patch one;
+//  - among the admissible counts (up to four times the smallest) the one with the fewest wave-steps
+//    ceil(CTAs / SMs) x (tiles_per_split + 0.5): a rank's share of a sharded giant bag is ~118 row blocks, and eight
+//    splits of 235 tiles were 6.4 waves = seven steps of 235 where ten splits of 188 are eight full steps of 188 (-8 %).
+void modularity_sweep_plan(int own_len, int max_len, int B, int* nsplit_out, int* tiles_per_split_out) {
+  const int sms = imp_num_sms();
+  const int row_blocks = (own_len + kBM - 1) / kBM;
+  const int col_tiles = (max_len + kBN - 1) / kBN + 1;        // absolute tiles: a bag may straddle one more
+  static const int max_tiles = []() { const char* e = getenv("IMP_SWEEP_MAXTILES"); return e && atoi(e) > 0 ? atoi(e) : 256; }();
+  const int ns_cap = std::max(1, col_tiles / 16);
+  int ns_min = std::max(1, std::min((2 * sms + row_blocks * B - 1) / (row_blocks * B), ns_cap));     // >= 2 waves
+  ns_min = std::max(ns_min, (col_tiles + max_tiles - 1) / max_tiles);
+  const int ns_max = std::max(ns_min, std::min(4 * ns_min, ns_cap));
+  long best_cost = -1;
+  int best_ns = ns_min, best_tps = (col_tiles + ns_min - 1) / ns_min;
+  for (int ns = ns_min; ns <= ns_max; ++ns) {
+    const int tps = (col_tiles + ns - 1) / ns;
+    const int ns_eff = (col_tiles + tps - 1) / tps;
+    const long ctas = (long)row_blocks * B * ns_eff;
+    const long cost = ((ctas + sms - 1) / sms) * (2L * tps + 1);
+    // a different split must buy at least 2 % (the wave model ignores that CTAs of a partial last wave overlap the previous one)
+    if (best_cost < 0 || cost * 100 < best_cost * 98) { best_cost = cost; best_ns = ns_eff; best_tps = tps; }
+  }
+  *nsplit_out = best_ns;
+  *tiles_per_split_out = best_tps;
+}
+
+namespace {
+
 int quads1(int P1) { return P1 <= 8 ? 2 : (P1 <= 16 ? 4 : 8); }
 int quads2(int P2) { return P2 == 0 ? 0 : 2; }
 
@@ -1278,14 +1312,8 @@ int launch_modularity_execute(const bf16* h_local, int local_rows, int row_lo, i
     gp.row_lo = whole ? 0 : row_lo; gp.row_hi = whole ? INT_MAX : row_lo + local_rows;
     const int row_blocks = (own_len + kBM - 1) / kBM;
     const int col_tiles = (max_len + kBN - 1) / kBN + 1;        // absolute tiles: a bag may straddle one more
-    // enough CTAs for >= 2 waves; at least 16 column tiles per CTA to amortise the A block load
-    int nsplit = std::max(1, std::min((2 * imp_num_sms() + row_blocks * B - 1) / (row_blocks * B), std::max(1, col_tiles / 16)));
-    // a CTA accumulates T_i over its own columns in 32-bit fixed point whose scale is set by the column count: at most
-    // 16 384 columns (256 tiles) per CTA keeps the resolution of a 120 000-patch bag at that of a 16 384-patch one
-    static const int max_tiles = []() { const char* e = getenv("IMP_SWEEP_MAXTILES"); return e && atoi(e) > 0 ? atoi(e) : 256; }();
-    nsplit = std::max(nsplit, (col_tiles + max_tiles - 1) / max_tiles);
-    gp.tiles_per_split = (col_tiles + nsplit - 1) / nsplit;
-    nsplit = (col_tiles + gp.tiles_per_split - 1) / gp.tiles_per_split;
+    int nsplit;
+    modularity_sweep_plan(own_len, max_len, B, &nsplit, &gp.tiles_per_split);
     const dim3 grid(row_blocks, nsplit, B);
 #define IMP_SWEEP(a, b2) rc = run_sweep<a, b2>(ta, tb, gp, grid, st)
     if (nq2 == 0) { if (nq1 == 2) IMP_SWEEP(2, 0); else if (nq1 == 4) IMP_SWEEP(4, 0); else IMP_SWEEP(8, 0); }

@@ -85,3 +85,39 @@ def test_pool_split_plan_fills_whole_waves(max_len, n_proto):
         assert waves * (tiles_per_cta + 1) == best, (bags, nsplit, waves, tiles_per_cta, best)
         if ctas > slots:
             assert ctas / (waves * slots) > 0.6, (bags, nsplit, ctas)
+
+
+def test_modularity_sweep_plan_bounds_and_waves():
+    """Pair-sweep column split (modularity.cu): >= 16 and <= 256 column tiles per CTA, every column tile covered, and no
+    admissible split count (up to 4x the smallest) beats the chosen one by more than 2 % in wave-steps on the 148-SM
+    default.  The sharded giant bag (15 000 of 120 000 rows on one rank) must not end in a 0.4-full seventh wave."""
+    from imp_b200 import _lib
+    lib = _lib.lib()
+    sms = 148
+
+    def plan(own, max_len, bags):
+        ns, tps = ctypes.c_int(), ctypes.c_int()
+        assert lib.imp_modularity_sweep_plan(own, max_len, bags, ctypes.byref(ns), ctypes.byref(tps)) == 0
+        return ns.value, tps.value
+
+    def steps(own, max_len, bags, ns):
+        col_tiles = -(-max_len // 64) + 1
+        tps = -(-col_tiles // ns)
+        ns_eff = -(-col_tiles // tps)
+        return -(-(-(-own // 128) * bags * ns_eff) // sms) * (2 * tps + 1)
+
+    for own, max_len, bags in [(16384, 16384, 32), (120000, 120000, 1), (15000, 120000, 1), (60000, 120000, 1),
+                               (4096, 4096, 8), (700, 700, 3), (100, 100, 1), (16384, 16384, 1)]:
+        ns, tps = plan(own, max_len, bags)
+        col_tiles = -(-max_len // 64) + 1
+        assert ns >= 1 and ns * tps >= col_tiles and (ns - 1) * tps < col_tiles, (own, max_len, bags, ns, tps)
+        assert tps <= 256 or col_tiles <= 256
+        assert tps >= min(16, col_tiles) - 1, (own, max_len, bags, ns, tps)
+        ns_min = max(1, -(-col_tiles // 256), min(-(-2 * sms // (-(-own // 128) * bags)), max(1, col_tiles // 16)))
+        mine = steps(own, max_len, bags, ns)
+        for alt in range(ns_min, max(ns_min, min(4 * ns_min, max(1, col_tiles // 16))) + 1):
+            assert mine * 98 <= steps(own, max_len, bags, alt) * 100 + 98, (own, max_len, bags, ns, alt)
+    ns, tps = plan(15000, 120000, 1)
+    ctas = -(-15000 // 128) * ns
+    assert ctas / (-(-ctas // sms) * sms) > 0.95, (ns, tps, ctas)
+    assert lib.imp_modularity_sweep_plan(0, 10, 1, None, None) != 0
