@@ -171,6 +171,21 @@ int imp_kmeans_update(const float* x, const int* assign, int n, int dim, int k, 
 int imp_lse_merge(const float* part_pooled, const float* part_lse, int n_bags, int n_parts, int n_proto,
                   float* pooled, float* lse, float* scratch, void* stream);
 
+/* N1  token-level tail: the core of NystromAttention for sequences shorter than the landmark count
+ * (medmm/modeling/ops/attention.py:105-127 with moore_penrose_iter_pinv, ops/utils.py:116-131), on the reduced
+ * matrices M(A) of imp_b200.token_tail.nystrom_short: for each of n_mat (slide, head) pairs
+ *   Z_0 = s M^T;  Z_{k+1} = 1/4 Z_k (13 I - M Z_k (15 I - M Z_k (7 I - M Z_k))), k < iters (<= 8);
+ *   y = rows 1.. of M (Z (M [0; v])).
+ * mat (n_mat, n_dim, n_dim) fp32 with n_dim = tokens + 1 <= 48; inv_scale: ONE device float s (the reference's
+ * 1 / (max row-sum * max column-sum) over the whole batch); v, y (n_mat, n_dim - 1, head_dim) fp32, head_dim 32 or 64.
+ * One CTA per matrix, everything in shared memory. */
+int imp_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, int n_mat, int n_dim, int head_dim,
+                         int iters, float* y, void* stream);
+/* Backward of the above: dy (n_mat, n_dim-1, head_dim) -> dmat (n_mat, n_dim, n_dim), dv like v, dscale (n_mat)
+ * partial derivatives wrt s (the caller sums them).  The Z_k are recomputed. */
+int imp_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy, int n_mat,
+                         int n_dim, int head_dim, int iters, float* dmat, float* dscale, float* dv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -306,3 +306,18 @@ extern "C" int imp_lse_merge(const float* part_pooled, const float* part_lse, in
   if (!part_pooled || !part_lse || !pooled || !lse || !scratch) IMP_FAIL(IMP_ERR_ARG, "imp_lse_merge: null pointer");
   return launch_lse_merge(part_pooled, part_lse, n_bags, n_parts, n_proto, pooled, lse, scratch, ST(stream));
 }
+
+// ------------------------------------------------------------------------------------------
+// N1 token tail: Nystrom attention core on the reduced matrices
+// ------------------------------------------------------------------------------------------
+extern "C" int imp_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, int n_mat, int n_dim,
+                                    int head_dim, int iters, float* y, void* stream) {
+  if (!mat || !inv_scale || !v || !y) IMP_FAIL(IMP_ERR_ARG, "imp_nystrom_core_fwd: null pointer");
+  return launch_nystrom_core_fwd(mat, inv_scale, v, n_mat, n_dim, head_dim, iters, y, ST(stream));
+}
+extern "C" int imp_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy, int n_mat,
+                                    int n_dim, int head_dim, int iters, float* dmat, float* dscale, float* dv,
+                                    void* stream) {
+  if (!mat || !inv_scale || !v || !dy || !dmat || !dscale || !dv) IMP_FAIL(IMP_ERR_ARG, "imp_nystrom_core_bwd: null pointer");
+  return launch_nystrom_core_bwd(mat, inv_scale, v, dy, n_mat, n_dim, head_dim, iters, dmat, dscale, dv, ST(stream));
+}

@@ -56,3 +56,9 @@ int launch_kmeans_update(const float* x, const int* assign, int N, int D, int K,
                          cudaStream_t st);
 int launch_lse_merge(const float* part_pooled, const float* part_lse, int B, int nsplit, int P, float* pooled,
                      float* lse, float* scratch, cudaStream_t st);
+
+// nystrom.cu
+int launch_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, int BH, int N, int d, int iters,
+                            float* y, cudaStream_t st);
+int launch_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy, int BH, int N,
+                            int d, int iters, float* dmat, float* dscale, float* dv, cudaStream_t st);

@@ -1,0 +1,279 @@
+// N1  Nystrom attention core of the token-level tail (reference: medmm/modeling/ops/attention.py:105-127,
+//     moore_penrose_iter_pinv ops/utils.py:116-131), on the reduced (n+1) x (n+1) matrices of token_tail.nystrom_short.
+//
+//   forward :  Z_0 = s A^T ;  Z_{k+1} = 1/4 Z_k (13 I - A Z_k (15 I - A Z_k (7 I - A Z_k)))   (k < iters)
+//              y   = rows 1..n of  A (Z_iters (A [0 ; v]))
+//   backward:  dA, ds (one partial per matrix), dv  from dy, with the Z_k recomputed in shared memory
+//
+// A is (n+1) x (n+1) with n <= 47 tokens, v is n x d (d = 32 or 64): ~30 matrix products of 41^3 per (slide, head)
+// forward and ~100 backward.  As batched library calls that is ~85 GEMM launches and ~100 element-wise launches per
+// attention layer and training step, seven layers per step: most of the token tail's launches.  Here one CTA owns
+// one (slide, head), keeps every matrix in shared memory and runs the whole chain: two launches per layer and step.
+// fp32 FMA on 2 x 2 register tiles (the products are far too small for the tensor core and the iteration wants fp32).
+#include "common.cuh"
+#include "launchers.h"
+
+namespace {
+
+constexpr int kNyThreads = 512;
+constexpr int kNyMaxN = 48;          // n + 1 rounded up to even
+
+// C (n x m) = diag * I_{ndiag} + alpha * op(A) op(B) (+ C when ACC); op(A) is n x kd, op(B) is kd x m.
+// n and m are even; every matrix is zero outside its real rows / columns, so no bounds are checked.
+template <bool TA, bool TB, bool ACC>
+__device__ __forceinline__ void mm(float* __restrict__ C, int ldc, const float* __restrict__ A, int lda,
+                                   const float* __restrict__ B, int ldb, int n, int m, int kd, float alpha,
+                                   float diag = 0.f, int ndiag = 0) {
+  const int tm = m >> 1, tiles = (n >> 1) * tm;
+  for (int t = threadIdx.x; t < tiles; t += kNyThreads) {
+    const int i = (t / tm) * 2, j = (t % tm) * 2;
+    float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < kd; ++k) {
+      const float a0 = TA ? A[k * lda + i] : A[i * lda + k];
+      const float a1 = TA ? A[k * lda + i + 1] : A[(i + 1) * lda + k];
+      const float b0 = TB ? B[j * ldb + k] : B[k * ldb + j];
+      const float b1 = TB ? B[(j + 1) * ldb + k] : B[k * ldb + j + 1];
+      c00 = fmaf(a0, b0, c00); c01 = fmaf(a0, b1, c01);
+      c10 = fmaf(a1, b0, c10); c11 = fmaf(a1, b1, c11);
+    }
+    float* c0 = C + i * ldc + j;
+    float* c1 = c0 + ldc;
+    float r00 = alpha * c00, r01 = alpha * c01, r10 = alpha * c10, r11 = alpha * c11;
+    if (i == j) {                      // 2 x 2 tiles are aligned with the diagonal
+      if (i < ndiag) r00 += diag;
+      if (i + 1 < ndiag) r11 += diag;
+    }
+    if (ACC) { r00 += c0[0]; r01 += c0[1]; r10 += c1[0]; r11 += c1[1]; }
+    c0[0] = r00; c0[1] = r01; c1[0] = r10; c1[1] = r11;
+  }
+}
+
+struct NyParams {
+  const float* mat;        // (BH, N, N)
+  const float* inv_scale;  // (1) device scalar s
+  const float* v;          // (BH, n, d)
+  const float* dy;         // (BH, n, d)            backward only
+  float* y;                // (BH, n, d)            forward only
+  float* dmat;             // (BH, N, N)
+  float* dv;               // (BH, n, d)
+  float* dscale;           // (BH) partial derivatives wrt s
+  int N, d, iters;
+};
+
+// A <- mat (zero padded), Z0 <- s A^T
+__device__ __forceinline__ void load_mat(const NyParams& p, float* A, float* Z0, int NP, int LD, float s) {
+  const float* src = p.mat + (size_t)blockIdx.x * p.N * p.N;
+  for (int idx = threadIdx.x; idx < NP * NP; idx += kNyThreads) {
+    const int i = idx / NP, j = idx - i * NP;
+    const float a = (i < p.N && j < p.N) ? __ldg(src + i * p.N + j) : 0.f;
+    A[i * LD + j] = a;
+    Z0[j * LD + i] = s * a;
+  }
+}
+// V1 <- [0 ; v] (row 0 and the padding rows are zero)
+__device__ __forceinline__ void load_rows(const float* src, float* V, int N, int NP, int d, int LDV) {
+  for (int idx = threadIdx.x; idx < NP * d; idx += kNyThreads) {
+    const int i = idx / d, c = idx - i * d;
+    V[i * LDV + c] = (i >= 1 && i < N) ? __ldg(src + (size_t)(i - 1) * d + c) : 0.f;
+  }
+}
+// one step of the iteration: Znext = 1/4 Z (13 I - AZ (15 I - AZ (7 I - AZ))); AZ, T1, T2 are scratch and hold
+// A Z, 7 I - A Z (overwritten by T3 = 13 I - ...) and 15 I - AZ T1 afterwards when KEEP (backward) is set
+__device__ __forceinline__ void ns_terms(const float* A, const float* Z, float* AZ, float* T1, float* T2, float* T3,
+                                         int N, int NP, int LD) {
+  mm<false, false, false>(AZ, LD, A, LD, Z, LD, NP, NP, NP, 1.f);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NP * NP; idx += kNyThreads) {
+    const int i = idx / NP, j = idx - i * NP;
+    T1[i * LD + j] = ((i == j && i < N) ? 7.f : 0.f) - AZ[i * LD + j];
+  }
+  __syncthreads();
+  mm<false, false, false>(T2, LD, AZ, LD, T1, LD, NP, NP, NP, -1.f, 15.f, N);
+  __syncthreads();
+  mm<false, false, false>(T3, LD, AZ, LD, T2, LD, NP, NP, NP, -1.f, 13.f, N);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kNyThreads, 1) nystrom_core_fwd_kernel(const NyParams p) {
+  extern __shared__ float ny_smem[];
+  const int N = p.N, NP = (N + 1) & ~1, LD = NP + 1, d = p.d, LDV = d + 1;
+  const int MS = NP * LD;
+  float* A = ny_smem;
+  float* Z = A + MS;
+  float* Zn = Z + MS;
+  float* AZ = Zn + MS;
+  float* T1 = AZ + MS;
+  float* T2 = T1 + MS;
+  float* T3 = T2 + MS;
+  float* V1 = T3 + MS;
+  float* W1 = V1 + NP * LDV;
+  float* W2 = W1 + NP * LDV;
+  const float s = __ldg(p.inv_scale);
+  load_mat(p, A, Z, NP, LD, s);
+  load_rows(p.v + (size_t)blockIdx.x * (N - 1) * d, V1, N, NP, d, LDV);
+  __syncthreads();
+  for (int k = 0; k < p.iters; ++k) {
+    ns_terms(A, Z, AZ, T1, T2, T3, N, NP, LD);
+    mm<false, false, false>(Zn, LD, Z, LD, T3, LD, NP, NP, NP, 0.25f);
+    __syncthreads();
+    float* t = Z; Z = Zn; Zn = t;
+  }
+  mm<false, false, false>(W1, LDV, A, LD, V1, LDV, NP, d, NP, 1.f);
+  __syncthreads();
+  mm<false, false, false>(W2, LDV, Z, LD, W1, LDV, NP, d, NP, 1.f);
+  __syncthreads();
+  mm<false, false, false>(W1, LDV, A, LD, W2, LDV, NP, d, NP, 1.f);        // W1 is free again: Y
+  __syncthreads();
+  float* dst = p.y + (size_t)blockIdx.x * (N - 1) * d;
+  for (int idx = threadIdx.x; idx < (N - 1) * d; idx += kNyThreads) {
+    const int i = idx / d, c = idx - i * d;
+    dst[idx] = W1[(i + 1) * LDV + c];
+  }
+}
+
+__global__ void __launch_bounds__(kNyThreads, 1) nystrom_core_bwd_kernel(const NyParams p) {
+  extern __shared__ float ny_smem[];
+  const int N = p.N, NP = (N + 1) & ~1, LD = NP + 1, d = p.d, LDV = d + 1;
+  const int MS = NP * LD, VS = NP * LDV;
+  float* A = ny_smem;
+  float* Zs = A + MS;                            // Z_0 .. Z_iters
+  float* G = Zs + (size_t)(p.iters + 1) * MS;    // dZ_{k+1}
+  float* Gn = G + MS;                            // dZ_k
+  float* dA = Gn + MS;
+  float* AZ = dA + MS;                           // scratch of the iteration; the final stage's vectors alias it
+  float* T1 = AZ + MS;
+  float* T2 = T1 + MS;
+  float* T3 = T2 + MS;
+  float* dAZ = T3 + MS;
+  float* X1 = dAZ + MS;
+  float* X2 = X1 + MS;
+  // the six NP x d vectors of the final stage live inside the seven scratch matrices when they fit (the usual case:
+  // 38 + 1 tokens, d = 32), behind them otherwise (a handful of tokens)
+  float* V1 = (6 * VS <= 7 * MS) ? AZ : X2 + MS;
+  float* W1 = V1 + VS;
+  float* W2 = W1 + VS;
+  float* dY = W2 + VS;
+  float* dW1 = dY + VS;
+  float* dW2 = dW1 + VS;
+  const float s = __ldg(p.inv_scale);
+  load_mat(p, A, Zs, NP, LD, s);
+  __syncthreads();
+  // ---- forward again, keeping every Z_k ----
+  for (int k = 0; k < p.iters; ++k) {
+    const float* Z = Zs + (size_t)k * MS;
+    ns_terms(A, Z, AZ, T1, T2, T3, N, NP, LD);
+    mm<false, false, false>(Zs + (size_t)(k + 1) * MS, LD, Z, LD, T3, LD, NP, NP, NP, 0.25f);
+    __syncthreads();
+  }
+  const float* Zl = Zs + (size_t)p.iters * MS;
+  // ---- y = A (Z (A V1)) ----
+  load_rows(p.v + (size_t)blockIdx.x * (N - 1) * d, V1, N, NP, d, LDV);
+  load_rows(p.dy + (size_t)blockIdx.x * (N - 1) * d, dY, N, NP, d, LDV);
+  __syncthreads();
+  mm<false, false, false>(W1, LDV, A, LD, V1, LDV, NP, d, NP, 1.f);
+  __syncthreads();
+  mm<false, false, false>(W2, LDV, Zl, LD, W1, LDV, NP, d, NP, 1.f);
+  mm<true, false, false>(dW2, LDV, A, LD, dY, LDV, NP, d, NP, 1.f);         // dW2 = A^T dY
+  __syncthreads();
+  mm<false, true, false>(dA, LD, dY, LDV, W2, LDV, NP, NP, d, 1.f);         // dA  = dY W2^T
+  mm<false, true, false>(G, LD, dW2, LDV, W1, LDV, NP, NP, d, 1.f);         // dZ  = dW2 W1^T
+  mm<true, false, false>(dW1, LDV, Zl, LD, dW2, LDV, NP, d, NP, 1.f);       // dW1 = Z^T dW2
+  __syncthreads();
+  mm<false, true, true>(dA, LD, dW1, LDV, V1, LDV, NP, NP, d, 1.f);         // dA += dW1 V1^T
+  mm<true, false, false>(W2, LDV, A, LD, dW1, LDV, NP, d, NP, 1.f);         // dV1 = A^T dW1 (W2 is free)
+  __syncthreads();
+  {
+    float* dst = p.dv + (size_t)blockIdx.x * (N - 1) * d;
+    for (int idx = threadIdx.x; idx < (N - 1) * d; idx += kNyThreads) {
+      const int i = idx / d, c = idx - i * d;
+      dst[idx] = W2[(i + 1) * LDV + c];
+    }
+  }
+  __syncthreads();                                // the vectors are dead: the scratch matrices may be overwritten
+  // ---- the iteration, backwards ----
+  for (int k = p.iters - 1; k >= 0; --k) {
+    const float* Z = Zs + (size_t)k * MS;
+    ns_terms(A, Z, AZ, T1, T2, T3, N, NP, LD);    // AZ, T1 = 7I - AZ, T2 = 15I - AZ T1, T3 = 13I - AZ T2
+    mm<false, true, false>(Gn, LD, G, LD, T3, LD, NP, NP, NP, 0.25f);       // dZ_k  = 1/4 G T3^T
+    mm<true, false, false>(X1, LD, Z, LD, G, LD, NP, NP, NP, 0.25f);        // dT3   = 1/4 Z^T G
+    __syncthreads();
+    mm<false, true, false>(dAZ, LD, X1, LD, T2, LD, NP, NP, NP, -1.f);      // dAZ   = -dT3 T2^T
+    mm<true, false, false>(X2, LD, AZ, LD, X1, LD, NP, NP, NP, -1.f);       // dT2   = -AZ^T dT3
+    __syncthreads();
+    mm<false, true, true>(dAZ, LD, X2, LD, T1, LD, NP, NP, NP, -1.f);       // dAZ  -= dT2 T1^T
+    mm<true, false, false>(X1, LD, AZ, LD, X2, LD, NP, NP, NP, -1.f);       // dT1   = -AZ^T dT2
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NP * NP; idx += kNyThreads) {
+      const int i = idx / NP, j = idx - i * NP;
+      dAZ[i * LD + j] -= X1[i * LD + j];                                    // AZ enters T1 with a minus sign
+    }
+    __syncthreads();
+    mm<false, true, true>(dA, LD, dAZ, LD, Z, LD, NP, NP, NP, 1.f);         // dA   += dAZ Z^T
+    mm<true, false, true>(Gn, LD, A, LD, dAZ, LD, NP, NP, NP, 1.f);         // dZ_k += A^T dAZ
+    __syncthreads();
+    float* t = G; G = Gn; Gn = t;
+  }
+  // ---- Z_0 = s A^T ----
+  float part = 0.f;
+  float* dst = p.dmat + (size_t)blockIdx.x * N * N;
+  for (int idx = threadIdx.x; idx < N * N; idx += kNyThreads) {
+    const int i = idx / N, j = idx - i * N;
+    const float g = G[j * LD + i];                // dZ_0[j][i] multiplies A[i][j]
+    dst[idx] = dA[i * LD + j] + s * g;
+    part = fmaf(g, A[i * LD + j], part);
+  }
+  part = warp_sum(part);
+  __shared__ float s_part[kNyThreads / 32];
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kNyThreads / 32; ++w) t += s_part[w];
+    p.dscale[blockIdx.x] = t;
+  }
+}
+
+size_t ny_fwd_smem(int N, int d) {
+  const int NP = (N + 1) & ~1;
+  return ((size_t)7 * NP * (NP + 1) + (size_t)3 * NP * (d + 1)) * sizeof(float);
+}
+size_t ny_bwd_smem(int N, int d, int iters) {
+  const int NP = (N + 1) & ~1;
+  const size_t MS = (size_t)NP * (NP + 1), VS = (size_t)NP * (d + 1);
+  return ((size_t)(iters + 12) * MS + (6 * VS <= 7 * MS ? 0 : 6 * VS)) * sizeof(float);
+}
+
+int ny_check(int BH, int N, int d, int iters, const char* who) {
+  if (BH <= 0 || N < 2 || iters < 0) IMP_FAIL(IMP_ERR_ARG, "%s: sizes must be positive (BH %d, N %d, iters %d)", who, BH, N, iters);
+  if (((N + 1) & ~1) > kNyMaxN) IMP_FAIL(IMP_ERR_ARG, "%s: at most %d tokens per matrix (got N = %d)", who, kNyMaxN - 1, N);
+  if (d != 32 && d != 64) IMP_FAIL(IMP_ERR_ARG, "%s: head dim must be 32 or 64 (got %d)", who, d);
+  if (iters > 8) IMP_FAIL(IMP_ERR_ARG, "%s: at most 8 iterations (got %d)", who, iters);
+  return IMP_OK;
+}
+
+}  // namespace
+
+int launch_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, int BH, int N, int d, int iters,
+                            float* y, cudaStream_t st) {
+  { const int rc = ny_check(BH, N, d, iters, "nystrom_core_fwd"); if (rc) return rc; }
+  NyParams p{};
+  p.mat = mat; p.inv_scale = inv_scale; p.v = v; p.y = y; p.N = N; p.d = d; p.iters = iters;
+  const size_t smem = ny_fwd_smem(N, d);
+  { const int rc = imp_ensure_smem((const void*)nystrom_core_fwd_kernel, 227 * 1024 - 1024); if (rc) return rc; }
+  IMP_LAUNCH("nystrom_core_fwd", st, nystrom_core_fwd_kernel<<<BH, kNyThreads, smem, st>>>(p));
+  return IMP_OK;
+}
+
+int launch_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy, int BH, int N,
+                            int d, int iters, float* dmat, float* dscale, float* dv, cudaStream_t st) {
+  { const int rc = ny_check(BH, N, d, iters, "nystrom_core_bwd"); if (rc) return rc; }
+  NyParams p{};
+  p.mat = mat; p.inv_scale = inv_scale; p.v = v; p.dy = dy; p.dmat = dmat; p.dscale = dscale; p.dv = dv;
+  p.N = N; p.d = d; p.iters = iters;
+  const size_t smem = ny_bwd_smem(N, d, iters);
+  if (smem > 227 * 1024 - 1024) IMP_FAIL(IMP_ERR_ARG, "nystrom_core_bwd: N = %d with %d iterations needs %zu bytes of shared memory", N, iters, smem);
+  { const int rc = imp_ensure_smem((const void*)nystrom_core_bwd_kernel, 227 * 1024 - 1024); if (rc) return rc; }
+  IMP_LAUNCH("nystrom_core_bwd", st, nystrom_core_bwd_kernel<<<BH, kNyThreads, smem, st>>>(p));
+  return IMP_OK;
+}

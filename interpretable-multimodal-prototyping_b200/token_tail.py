@@ -68,6 +68,9 @@ def nystrom_short(q, k, v, m: int, iters: int):
     cs = torch.maximum((p / m + cvec.sum(-2)).max(), (p / m + dmat.sum(-2)).max())
     top = torch.cat([s.new_full(s.shape[:-2] + (1, 1), p / m), s.new_full(s.shape[:-2] + (1, n), rp / m)], dim=-1)
     mat = torch.cat([top, torch.cat([rp * cvec, dmat], dim=-1)], dim=-2)          # M(A), (B,H,n+1,n+1)
+    if mat.is_cuda and _core_supported(n + 1, v.shape[-1], iters):
+        # one kernel per direction instead of ~85 batched GEMMs and ~100 element-wise launches (csrc/nystrom.cu)
+        return _NystromCore.apply(mat, 1.0 / (rs * cs), v, iters)
     eye = torch.eye(n + 1, device=s.device, dtype=s.dtype)
     z = mat.transpose(-1, -2) / (rs * cs)
     for _ in range(iters):
@@ -75,6 +78,45 @@ def nystrom_short(q, k, v, m: int, iters: int):
         z = 0.25 * z @ (13 * eye - az @ (15 * eye - az @ (7 * eye - az)))
     v1 = F.pad(v, (0, 0, 1, 0))                                  # coordinates of [0; v]: zero along u
     return (mat @ (z @ (mat @ v1)))[..., 1:, :]
+
+
+def _core_supported(n_dim: int, head_dim: int, iters: int) -> bool:
+    """Shapes csrc/nystrom.cu holds in shared memory; anything else (more than 47 tokens: P = 64 prototypes) keeps
+    the batched form above."""
+    return n_dim <= 48 and head_dim in (32, 64) and 0 <= iters <= 8
+
+
+class _NystromCore(torch.autograd.Function):
+    """y = rows 1.. of M (pinv_iter(M) (M [0; v])) with the iteration's initial scale as a tensor argument, so that the
+    gradient the reference sends through ``torch.max`` of the row / column sums (ops/utils.py:119-121) is kept."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, mat, inv_scale, v, iters):
+        from . import _lib
+        mat, v = mat.contiguous(), v.contiguous()
+        inv_scale = inv_scale.reshape(1).contiguous()
+        n_dim, d = mat.shape[-1], v.shape[-1]
+        n_mat = mat.numel() // (n_dim * n_dim)
+        y = torch.empty_like(v)
+        _lib.call("imp_nystrom_core_fwd", mat, inv_scale, v, n_mat, n_dim, d, int(iters), y, _lib.stream_ptr())
+        ctx.save_for_backward(mat, inv_scale, v)
+        ctx.iters = int(iters)
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        from . import _lib
+        mat, inv_scale, v = ctx.saved_tensors
+        n_dim, d = mat.shape[-1], v.shape[-1]
+        n_mat = mat.numel() // (n_dim * n_dim)
+        dy = dy.contiguous().float()
+        dmat, dv = torch.empty_like(mat), torch.empty_like(v)
+        dscale = torch.empty(n_mat, device=mat.device, dtype=torch.float32)
+        _lib.call("imp_nystrom_core_bwd", mat, inv_scale, v, dy, n_mat, n_dim, d, ctx.iters, dmat, dscale, dv,
+                  _lib.stream_ptr())
+        return dmat, dscale.sum().reshape(()), dv, None
 
 
 class NystromAttention(nn.Module):

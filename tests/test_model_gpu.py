@@ -174,3 +174,39 @@ def test_umeml_matches_reference():
         L.add("grad(logits^2 + modularity) " + k, rel(named[k].grad, z["train.grad." + k]), 5e-1, "executed reference",
               "ill-conditioned: the fp64 oracle itself moves by 0.33 under the same input rounding")
     L.assert_ok()
+
+
+
+def test_captured_step_matches_eager(tmp_path, monkeypatch):
+    """The whole model step captured in one CUDA graph (``GraphedStep.capture_fn``, importance rows deferred): the
+    replayed loss and gradients equal the eager step (dropout 0, same parameters)."""
+    monkeypatch.chdir(tmp_path)
+    from imp_b200 import step as S, survival
+    dev = torch.device("cuda")
+    z = load()
+    model = build(z).to(dev).train()
+    model.importance_log = "defer"
+    model.p_proto = model.p_proto.to(dev)
+    batch = _batch(z, dev)
+    y, c = z["label"].to(dev), z["censorship"].to(dev)
+    params = list(model.parameters())
+
+    def loss_fn():
+        out = model(batch)
+        return survival.nll_loss_new(out, y, c) + out[5] + out[1]
+
+    for p in params:
+        p.grad = None
+    loss_eager = loss_fn()
+    loss_eager.backward()
+    ref = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    loss_eager = float(loss_eager)
+    gs = S.GraphedStep(None).capture_fn(loss_fn, params, dev)
+    for _ in range(2):
+        loss = gs.replay()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - loss_eager) <= 1e-5 * abs(loss_eager)
+    for k, p in model.named_parameters():
+        if k in ref:
+            assert rel(p.grad, ref[k]) < 1e-4, (k, rel(p.grad, ref[k]))
+    gs.close()
