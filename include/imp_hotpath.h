@@ -178,13 +178,17 @@ int imp_lse_merge(const float* part_pooled, const float* part_lse, int n_bags, i
  *   y = rows 1.. of M (Z (M [0; v])).
  * mat (n_mat, n_dim, n_dim) fp32 with n_dim = tokens + 1 <= 48; inv_scale: ONE device float s (the reference's
  * 1 / (max row-sum * max column-sum) over the whole batch); v, y (n_mat, n_dim - 1, head_dim) fp32, head_dim 32 or 64.
- * One CTA per matrix, everything in shared memory. */
+ * One CTA per matrix, everything in shared memory.  saved (may be NULL): n_mat * imp_nystrom_core_saved_floats(n_dim,
+ * iters) floats that receive the iterates Z_0..Z_iters for the backward call. */
+size_t imp_nystrom_core_saved_floats(int n_dim, int iters);
 int imp_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, int n_mat, int n_dim, int head_dim,
-                         int iters, float* y, void* stream);
+                         int iters, float* y, float* saved, void* stream);
 /* Backward of the above: dy (n_mat, n_dim-1, head_dim) -> dmat (n_mat, n_dim, n_dim), dv like v, dscale (n_mat)
- * partial derivatives wrt s (the caller sums them).  The Z_k are recomputed. */
-int imp_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy, int n_mat,
-                         int n_dim, int head_dim, int iters, float* dmat, float* dscale, float* dv, void* stream);
+ * partial derivatives wrt s (the caller sums them).  saved: the buffer the forward call filled, or NULL (the iteration
+ * is then run again). */
+int imp_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy, const float* saved,
+                         int n_mat, int n_dim, int head_dim, int iters, float* dmat, float* dscale, float* dv,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -49,7 +49,7 @@ def lib() -> ctypes.CDLL:
             raise ImpError("libimp_sm100.so reports ABI %d, include/imp_hotpath.h declares %d: rebuild the library" % (got, want))
         for name in header_symbols():
             fn = getattr(_lib, name)          # AttributeError if the .so lacks a declared symbol
-            if name.endswith("_bytes"):
+            if name.endswith(("_bytes", "_floats")):
                 fn.restype = ctypes.c_size_t
     return _lib
 

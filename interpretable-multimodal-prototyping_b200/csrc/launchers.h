@@ -58,7 +58,8 @@ int launch_lse_merge(const float* part_pooled, const float* part_lse, int B, int
                      float* lse, float* scratch, cudaStream_t st);
 
 // nystrom.cu
+size_t nystrom_core_saved_floats(int N, int iters);
 int launch_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, int BH, int N, int d, int iters,
-                            float* y, cudaStream_t st);
-int launch_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy, int BH, int N,
-                            int d, int iters, float* dmat, float* dscale, float* dv, cudaStream_t st);
+                            float* y, float* zs, cudaStream_t st);
+int launch_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy, const float* zs,
+                            int BH, int N, int d, int iters, float* dmat, float* dscale, float* dv, cudaStream_t st);

@@ -15,37 +15,55 @@
 
 namespace {
 
-constexpr int kNyThreads = 512;
-constexpr int kNyMaxN = 48;          // n + 1 rounded up to even
+constexpr int kNyThreads = 512;        // four groups of 128 threads
+constexpr int kNyMaxN = 48;          // n + 1 rounded up to a multiple of 4
 
 // C (n x m) = diag * I_{ndiag} + alpha * op(A) op(B) (+ C when ACC); op(A) is n x kd, op(B) is kd x m.
-// n and m are even; every matrix is zero outside its real rows / columns, so no bounds are checked.
+// n and m are multiples of 4; every matrix is zero outside its real rows / columns, so no bounds are checked.
+// 4 x 4 register tiles: 8 shared-memory loads per 16 FMAs (2 x 2 tiles, one load per FMA: backward 224 -> 197 us, forward
+// 69 -> 51 us per layer at 32 slides x 8 heads, 39 tokens).  A software-pipelined variant (register ping-pong, 256
+// threads, 255 registers, one CTA per SM) measured slower (232 / 92 us): the products are bound by shared-memory
+// wavefronts (12 per k step and warp with the 44-word rows wrapping the 32 banks), not by load latency.
 template <bool TA, bool TB, bool ACC>
 __device__ __forceinline__ void mm(float* __restrict__ C, int ldc, const float* __restrict__ A, int lda,
                                    const float* __restrict__ B, int ldb, int n, int m, int kd, float alpha,
-                                   float diag = 0.f, int ndiag = 0) {
-  const int tm = m >> 1, tiles = (n >> 1) * tm;
-  for (int t = threadIdx.x; t < tiles; t += kNyThreads) {
-    const int i = (t / tm) * 2, j = (t % tm) * 2;
-    float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
-#pragma unroll 4
+                                   float diag = 0.f, int ndiag = 0, int grp = 0) {
+  // one group of 128 threads per product (<= 144 tiles): independent products of a phase run side by side on
+  // different groups and hide each other's shared-memory latency
+  if ((int)(threadIdx.x >> 7) != grp) return;
+  const int tm = m >> 2, tiles = (n >> 2) * tm;
+  for (int t = threadIdx.x & 127; t < tiles; t += 128) {
+    const int i = (t / tm) * 4, j = (t % tm) * 4;
+    float c[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[r][q] = 0.f;
+    const float* ap = TA ? A + i : A + i * lda;
+    const float* bp = TB ? B + j * ldb : B + j;
+#pragma unroll 2
     for (int k = 0; k < kd; ++k) {
-      const float a0 = TA ? A[k * lda + i] : A[i * lda + k];
-      const float a1 = TA ? A[k * lda + i + 1] : A[(i + 1) * lda + k];
-      const float b0 = TB ? B[j * ldb + k] : B[k * ldb + j];
-      const float b1 = TB ? B[(j + 1) * ldb + k] : B[k * ldb + j + 1];
-      c00 = fmaf(a0, b0, c00); c01 = fmaf(a0, b1, c01);
-      c10 = fmaf(a1, b0, c10); c11 = fmaf(a1, b1, c11);
+      float a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = TA ? ap[k * lda + r] : ap[r * lda + k];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) b[q] = TB ? bp[q * ldb + k] : bp[k * ldb + q];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[r][q] = fmaf(a[r], b[q], c[r][q]);
     }
-    float* c0 = C + i * ldc + j;
-    float* c1 = c0 + ldc;
-    float r00 = alpha * c00, r01 = alpha * c01, r10 = alpha * c10, r11 = alpha * c11;
-    if (i == j) {                      // 2 x 2 tiles are aligned with the diagonal
-      if (i < ndiag) r00 += diag;
-      if (i + 1 < ndiag) r11 += diag;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float* crow = C + (i + r) * ldc + j;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v = alpha * c[r][q];
+        if (i == j && r == q && i + r < ndiag) v += diag;      // 4 x 4 tiles are aligned with the diagonal
+        if (ACC) v += crow[q];
+        crow[q] = v;
+      }
     }
-    if (ACC) { r00 += c0[0]; r01 += c0[1]; r10 += c1[0]; r11 += c1[1]; }
-    c0[0] = r00; c0[1] = r01; c1[0] = r10; c1[1] = r11;
   }
 }
 
@@ -58,6 +76,8 @@ struct NyParams {
   float* dmat;             // (BH, N, N)
   float* dv;               // (BH, n, d)
   float* dscale;           // (BH) partial derivatives wrt s
+  float* zs;               // (BH, iters + 1, NP * (NP + 1)) the iterates Z_k in the shared-memory layout: written by the
+                           // forward (may be null), read by the backward instead of running the iteration again
   int N, d, iters;
 };
 
@@ -95,9 +115,9 @@ __device__ __forceinline__ void ns_terms(const float* A, const float* Z, float* 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kNyThreads, 1) nystrom_core_fwd_kernel(const NyParams p) {
+__global__ void __launch_bounds__(kNyThreads, 2) nystrom_core_fwd_kernel(const NyParams p) {
   extern __shared__ float ny_smem[];
-  const int N = p.N, NP = (N + 1) & ~1, LD = NP + 1, d = p.d, LDV = d + 1;
+  const int N = p.N, NP = (N + 3) & ~3, LD = NP + 1, d = p.d, LDV = d + 1;
   const int MS = NP * LD;
   float* A = ny_smem;
   float* Z = A + MS;
@@ -113,11 +133,17 @@ __global__ void __launch_bounds__(kNyThreads, 1) nystrom_core_fwd_kernel(const N
   load_mat(p, A, Z, NP, LD, s);
   load_rows(p.v + (size_t)blockIdx.x * (N - 1) * d, V1, N, NP, d, LDV);
   __syncthreads();
+  float* zdst = p.zs ? p.zs + (size_t)blockIdx.x * (p.iters + 1) * MS : nullptr;
+  auto keep = [&](const float* Zk, int k) {          // the padding column is never read: copy the buffer as it is
+    if (zdst) for (int idx = threadIdx.x; idx < MS; idx += kNyThreads) zdst[(size_t)k * MS + idx] = Zk[idx];
+  };
+  keep(Z, 0);
   for (int k = 0; k < p.iters; ++k) {
     ns_terms(A, Z, AZ, T1, T2, T3, N, NP, LD);
     mm<false, false, false>(Zn, LD, Z, LD, T3, LD, NP, NP, NP, 0.25f);
     __syncthreads();
     float* t = Z; Z = Zn; Zn = t;
+    keep(Z, k + 1);
   }
   mm<false, false, false>(W1, LDV, A, LD, V1, LDV, NP, d, NP, 1.f);
   __syncthreads();
@@ -134,7 +160,7 @@ __global__ void __launch_bounds__(kNyThreads, 1) nystrom_core_fwd_kernel(const N
 
 __global__ void __launch_bounds__(kNyThreads, 1) nystrom_core_bwd_kernel(const NyParams p) {
   extern __shared__ float ny_smem[];
-  const int N = p.N, NP = (N + 1) & ~1, LD = NP + 1, d = p.d, LDV = d + 1;
+  const int N = p.N, NP = (N + 3) & ~3, LD = NP + 1, d = p.d, LDV = d + 1;
   const int MS = NP * LD, VS = NP * LDV;
   float* A = ny_smem;
   float* Zs = A + MS;                            // Z_0 .. Z_iters
@@ -159,7 +185,12 @@ __global__ void __launch_bounds__(kNyThreads, 1) nystrom_core_bwd_kernel(const N
   const float s = __ldg(p.inv_scale);
   load_mat(p, A, Zs, NP, LD, s);
   __syncthreads();
-  // ---- forward again, keeping every Z_k ----
+  // ---- the iterates Z_k: from the forward launch when it kept them, else by running the iteration again ----
+  if (p.zs) {
+    const float* zsrc = p.zs + (size_t)blockIdx.x * (p.iters + 1) * MS;
+    for (int idx = threadIdx.x; idx < (p.iters + 1) * MS; idx += kNyThreads) Zs[idx] = __ldg(zsrc + idx);
+    __syncthreads();
+  } else
   for (int k = 0; k < p.iters; ++k) {
     const float* Z = Zs + (size_t)k * MS;
     ns_terms(A, Z, AZ, T1, T2, T3, N, NP, LD);
@@ -174,14 +205,14 @@ __global__ void __launch_bounds__(kNyThreads, 1) nystrom_core_bwd_kernel(const N
   mm<false, false, false>(W1, LDV, A, LD, V1, LDV, NP, d, NP, 1.f);
   __syncthreads();
   mm<false, false, false>(W2, LDV, Zl, LD, W1, LDV, NP, d, NP, 1.f);
-  mm<true, false, false>(dW2, LDV, A, LD, dY, LDV, NP, d, NP, 1.f);         // dW2 = A^T dY
+  mm<true, false, false>(dW2, LDV, A, LD, dY, LDV, NP, d, NP, 1.f, 0.f, 0, 1);         // dW2 = A^T dY
   __syncthreads();
   mm<false, true, false>(dA, LD, dY, LDV, W2, LDV, NP, NP, d, 1.f);         // dA  = dY W2^T
-  mm<false, true, false>(G, LD, dW2, LDV, W1, LDV, NP, NP, d, 1.f);         // dZ  = dW2 W1^T
-  mm<true, false, false>(dW1, LDV, Zl, LD, dW2, LDV, NP, d, NP, 1.f);       // dW1 = Z^T dW2
+  mm<false, true, false>(G, LD, dW2, LDV, W1, LDV, NP, NP, d, 1.f, 0.f, 0, 1);         // dZ  = dW2 W1^T
+  mm<true, false, false>(dW1, LDV, Zl, LD, dW2, LDV, NP, d, NP, 1.f, 0.f, 0, 2);       // dW1 = Z^T dW2
   __syncthreads();
   mm<false, true, true>(dA, LD, dW1, LDV, V1, LDV, NP, NP, d, 1.f);         // dA += dW1 V1^T
-  mm<true, false, false>(W2, LDV, A, LD, dW1, LDV, NP, d, NP, 1.f);         // dV1 = A^T dW1 (W2 is free)
+  mm<true, false, false>(W2, LDV, A, LD, dW1, LDV, NP, d, NP, 1.f, 0.f, 0, 1);         // dV1 = A^T dW1 (W2 is free)
   __syncthreads();
   {
     float* dst = p.dv + (size_t)blockIdx.x * (N - 1) * d;
@@ -196,13 +227,13 @@ __global__ void __launch_bounds__(kNyThreads, 1) nystrom_core_bwd_kernel(const N
     const float* Z = Zs + (size_t)k * MS;
     ns_terms(A, Z, AZ, T1, T2, T3, N, NP, LD);    // AZ, T1 = 7I - AZ, T2 = 15I - AZ T1, T3 = 13I - AZ T2
     mm<false, true, false>(Gn, LD, G, LD, T3, LD, NP, NP, NP, 0.25f);       // dZ_k  = 1/4 G T3^T
-    mm<true, false, false>(X1, LD, Z, LD, G, LD, NP, NP, NP, 0.25f);        // dT3   = 1/4 Z^T G
+    mm<true, false, false>(X1, LD, Z, LD, G, LD, NP, NP, NP, 0.25f, 0.f, 0, 1);        // dT3   = 1/4 Z^T G
     __syncthreads();
     mm<false, true, false>(dAZ, LD, X1, LD, T2, LD, NP, NP, NP, -1.f);      // dAZ   = -dT3 T2^T
-    mm<true, false, false>(X2, LD, AZ, LD, X1, LD, NP, NP, NP, -1.f);       // dT2   = -AZ^T dT3
+    mm<true, false, false>(X2, LD, AZ, LD, X1, LD, NP, NP, NP, -1.f, 0.f, 0, 1);       // dT2   = -AZ^T dT3
     __syncthreads();
     mm<false, true, true>(dAZ, LD, X2, LD, T1, LD, NP, NP, NP, -1.f);       // dAZ  -= dT2 T1^T
-    mm<true, false, false>(X1, LD, AZ, LD, X2, LD, NP, NP, NP, -1.f);       // dT1   = -AZ^T dT2
+    mm<true, false, false>(X1, LD, AZ, LD, X2, LD, NP, NP, NP, -1.f, 0.f, 0, 1);       // dT1   = -AZ^T dT2
     __syncthreads();
     for (int idx = threadIdx.x; idx < NP * NP; idx += kNyThreads) {
       const int i = idx / NP, j = idx - i * NP;
@@ -210,7 +241,7 @@ __global__ void __launch_bounds__(kNyThreads, 1) nystrom_core_bwd_kernel(const N
     }
     __syncthreads();
     mm<false, true, true>(dA, LD, dAZ, LD, Z, LD, NP, NP, NP, 1.f);         // dA   += dAZ Z^T
-    mm<true, false, true>(Gn, LD, A, LD, dAZ, LD, NP, NP, NP, 1.f);         // dZ_k += A^T dAZ
+    mm<true, false, true>(Gn, LD, A, LD, dAZ, LD, NP, NP, NP, 1.f, 0.f, 0, 1);         // dZ_k += A^T dAZ
     __syncthreads();
     float* t = G; G = Gn; Gn = t;
   }
@@ -235,18 +266,18 @@ __global__ void __launch_bounds__(kNyThreads, 1) nystrom_core_bwd_kernel(const N
 }
 
 size_t ny_fwd_smem(int N, int d) {
-  const int NP = (N + 1) & ~1;
+  const int NP = (N + 3) & ~3;
   return ((size_t)7 * NP * (NP + 1) + (size_t)3 * NP * (d + 1)) * sizeof(float);
 }
 size_t ny_bwd_smem(int N, int d, int iters) {
-  const int NP = (N + 1) & ~1;
+  const int NP = (N + 3) & ~3;
   const size_t MS = (size_t)NP * (NP + 1), VS = (size_t)NP * (d + 1);
   return ((size_t)(iters + 12) * MS + (6 * VS <= 7 * MS ? 0 : 6 * VS)) * sizeof(float);
 }
 
 int ny_check(int BH, int N, int d, int iters, const char* who) {
   if (BH <= 0 || N < 2 || iters < 0) IMP_FAIL(IMP_ERR_ARG, "%s: sizes must be positive (BH %d, N %d, iters %d)", who, BH, N, iters);
-  if (((N + 1) & ~1) > kNyMaxN) IMP_FAIL(IMP_ERR_ARG, "%s: at most %d tokens per matrix (got N = %d)", who, kNyMaxN - 1, N);
+  if (((N + 3) & ~3) > kNyMaxN) IMP_FAIL(IMP_ERR_ARG, "%s: at most %d tokens per matrix (got N = %d)", who, kNyMaxN - 1, N);
   if (d != 32 && d != 64) IMP_FAIL(IMP_ERR_ARG, "%s: head dim must be 32 or 64 (got %d)", who, d);
   if (iters > 8) IMP_FAIL(IMP_ERR_ARG, "%s: at most 8 iterations (got %d)", who, iters);
   return IMP_OK;
@@ -254,22 +285,28 @@ int ny_check(int BH, int N, int d, int iters, const char* who) {
 
 }  // namespace
 
+size_t nystrom_core_saved_floats(int N, int iters) {
+  const int NP = (N + 3) & ~3;
+  return (size_t)(iters + 1) * NP * (NP + 1);
+}
+
 int launch_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, int BH, int N, int d, int iters,
-                            float* y, cudaStream_t st) {
+                            float* y, float* zs, cudaStream_t st) {
   { const int rc = ny_check(BH, N, d, iters, "nystrom_core_fwd"); if (rc) return rc; }
   NyParams p{};
-  p.mat = mat; p.inv_scale = inv_scale; p.v = v; p.y = y; p.N = N; p.d = d; p.iters = iters;
+  p.mat = mat; p.inv_scale = inv_scale; p.v = v; p.y = y; p.zs = zs; p.N = N; p.d = d; p.iters = iters;
   const size_t smem = ny_fwd_smem(N, d);
   { const int rc = imp_ensure_smem((const void*)nystrom_core_fwd_kernel, 227 * 1024 - 1024); if (rc) return rc; }
   IMP_LAUNCH("nystrom_core_fwd", st, nystrom_core_fwd_kernel<<<BH, kNyThreads, smem, st>>>(p));
   return IMP_OK;
 }
 
-int launch_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy, int BH, int N,
-                            int d, int iters, float* dmat, float* dscale, float* dv, cudaStream_t st) {
+int launch_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy, const float* zs,
+                            int BH, int N, int d, int iters, float* dmat, float* dscale, float* dv, cudaStream_t st) {
   { const int rc = ny_check(BH, N, d, iters, "nystrom_core_bwd"); if (rc) return rc; }
   NyParams p{};
   p.mat = mat; p.inv_scale = inv_scale; p.v = v; p.dy = dy; p.dmat = dmat; p.dscale = dscale; p.dv = dv;
+  p.zs = const_cast<float*>(zs);
   p.N = N; p.d = d; p.iters = iters;
   const size_t smem = ny_bwd_smem(N, d, iters);
   if (smem > 227 * 1024 - 1024) IMP_FAIL(IMP_ERR_ARG, "nystrom_core_bwd: N = %d with %d iterations needs %zu bytes of shared memory", N, iters, smem);

@@ -99,8 +99,12 @@ class _NystromCore(torch.autograd.Function):
         n_dim, d = mat.shape[-1], v.shape[-1]
         n_mat = mat.numel() // (n_dim * n_dim)
         y = torch.empty_like(v)
-        _lib.call("imp_nystrom_core_fwd", mat, inv_scale, v, n_mat, n_dim, d, int(iters), y, _lib.stream_ptr())
-        ctx.save_for_backward(mat, inv_scale, v)
+        saved = None
+        if any(ctx.needs_input_grad[:3]):                     # the iterates Z_k, so that the backward does not repeat the iteration
+            saved = torch.empty(n_mat, _lib.query("imp_nystrom_core_saved_floats", n_dim, int(iters)), device=mat.device,
+                                dtype=torch.float32)
+        _lib.call("imp_nystrom_core_fwd", mat, inv_scale, v, n_mat, n_dim, d, int(iters), y, saved, _lib.stream_ptr())
+        ctx.save_for_backward(mat, inv_scale, v, saved)
         ctx.iters = int(iters)
         return y
 
@@ -108,13 +112,13 @@ class _NystromCore(torch.autograd.Function):
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dy):
         from . import _lib
-        mat, inv_scale, v = ctx.saved_tensors
+        mat, inv_scale, v, saved = ctx.saved_tensors
         n_dim, d = mat.shape[-1], v.shape[-1]
         n_mat = mat.numel() // (n_dim * n_dim)
         dy = dy.contiguous().float()
         dmat, dv = torch.empty_like(mat), torch.empty_like(v)
         dscale = torch.empty(n_mat, device=mat.device, dtype=torch.float32)
-        _lib.call("imp_nystrom_core_bwd", mat, inv_scale, v, dy, n_mat, n_dim, d, ctx.iters, dmat, dscale, dv,
+        _lib.call("imp_nystrom_core_bwd", mat, inv_scale, v, dy, saved, n_mat, n_dim, d, ctx.iters, dmat, dscale, dv,
                   _lib.stream_ptr())
         return dmat, dscale.sum().reshape(()), dv, None
 

@@ -73,4 +73,25 @@ def test_nystrom_core_rejects_unsupported_shapes():
     s = torch.ones(1, device="cuda")
     v = torch.zeros(2, 49, 32, device="cuda")
     with pytest.raises(_lib.ImpError):
-        _lib.call("imp_nystrom_core_fwd", mat, s, v, 2, 50, 32, 6, torch.empty_like(v), _lib.stream_ptr())
+        _lib.call("imp_nystrom_core_fwd", mat, s, v, 2, 50, 32, 6, torch.empty_like(v), None, _lib.stream_ptr())
+
+
+def test_nystrom_backward_with_and_without_kept_iterates():
+    """imp_nystrom_core_bwd with the iterates the forward kept and with saved = NULL (iteration repeated): same result."""
+    from imp_b200 import _lib
+    torch.manual_seed(5)
+    n_mat, n_dim, d, iters = 16, 39, 32, 6
+    mat = torch.softmax(torch.randn(n_mat, n_dim, n_dim, device="cuda"), -1)
+    s = (1.0 / (mat.abs().sum(-1).max() * mat.abs().sum(-2).max())).reshape(1)
+    v, dy = torch.randn(n_mat, n_dim - 1, d, device="cuda"), torch.randn(n_mat, n_dim - 1, d, device="cuda")
+    y = torch.empty_like(v)
+    saved = torch.empty(n_mat, _lib.query("imp_nystrom_core_saved_floats", n_dim, iters), device="cuda")
+    _lib.call("imp_nystrom_core_fwd", mat, s, v, n_mat, n_dim, d, iters, y, saved, _lib.stream_ptr())
+    res = []
+    for buf in (saved, None):
+        dmat, dv, ds = torch.empty_like(mat), torch.empty_like(v), torch.empty(n_mat, device="cuda")
+        _lib.call("imp_nystrom_core_bwd", mat, s, v, dy, buf, n_mat, n_dim, d, iters, dmat, ds, dv, _lib.stream_ptr())
+        res.append((dmat, dv, ds))
+    torch.cuda.synchronize()
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
