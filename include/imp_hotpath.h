@@ -172,23 +172,25 @@ int imp_lse_merge(const float* part_pooled, const float* part_lse, int n_bags, i
                   float* pooled, float* lse, float* scratch, void* stream);
 
 /* N1  token-level tail: the core of NystromAttention for sequences shorter than the landmark count
- * (medmm/modeling/ops/attention.py:105-127 with moore_penrose_iter_pinv, ops/utils.py:116-131), on the reduced
+ * (medmm/modeling/ops/attention.py:105-131 with moore_penrose_iter_pinv, ops/utils.py:116-131), on the reduced
  * matrices M(A) of imp_b200.token_tail.nystrom_short: for each of n_mat (slide, head) pairs
  *   Z_0 = s M^T;  Z_{k+1} = 1/4 Z_k (13 I - M Z_k (15 I - M Z_k (7 I - M Z_k))), k < iters (<= 8);
- *   y = rows 1.. of M (Z (M [0; v])).
+ *   y = rows 1.. of M (Z (M [0; v]))  +  res_conv(v)     (the depth-wise residual convolution of :129-131 when conv_w != NULL).
  * mat (n_mat, n_dim, n_dim) fp32 with n_dim = tokens + 1 <= 48; inv_scale: ONE device float s (the reference's
- * 1 / (max row-sum * max column-sum) over the whole batch); v, y (n_mat, n_dim - 1, head_dim) fp32, head_dim 32 or 64.
+ * 1 / (max row-sum * max column-sum) over the whole batch); v, y (n_mat, n_dim - 1, head_dim) fp32, head_dim 32 or 64;
+ * conv_w (heads, taps) fp32 or NULL, taps odd, matrix index = slide * heads + head.
  * One CTA per matrix, everything in shared memory.  saved (may be NULL): n_mat * imp_nystrom_core_saved_floats(n_dim,
  * iters) floats that receive the iterates Z_0..Z_iters for the backward call. */
 size_t imp_nystrom_core_saved_floats(int n_dim, int iters);
-int imp_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, int n_mat, int n_dim, int head_dim,
-                         int iters, float* y, float* saved, void* stream);
+int imp_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, const float* conv_w, int heads,
+                         int taps, int n_mat, int n_dim, int head_dim, int iters, float* y, float* saved, void* stream);
 /* Backward of the above: dy (n_mat, n_dim-1, head_dim) -> dmat (n_mat, n_dim, n_dim), dv like v, dscale (n_mat)
- * partial derivatives wrt s (the caller sums them).  saved: the buffer the forward call filled, or NULL (the iteration
- * is then run again). */
+ * partial derivatives wrt s and dconv (n_mat, taps) partial derivatives wrt conv_w (the caller sums them over the
+ * slides; dconv may be NULL when conv_w is).  saved: the buffer the forward call filled, or NULL (the iteration is
+ * then run again). */
 int imp_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy, const float* saved,
-                         int n_mat, int n_dim, int head_dim, int iters, float* dmat, float* dscale, float* dv,
-                         void* stream);
+                         const float* conv_w, int heads, int taps, int n_mat, int n_dim, int head_dim, int iters,
+                         float* dmat, float* dscale, float* dv, float* dconv, void* stream);
 
 #ifdef __cplusplus
 }

@@ -311,14 +311,17 @@ extern "C" int imp_lse_merge(const float* part_pooled, const float* part_lse, in
 // N1 token tail: Nystrom attention core on the reduced matrices
 // ------------------------------------------------------------------------------------------
 extern "C" size_t imp_nystrom_core_saved_floats(int n_dim, int iters) { return nystrom_core_saved_floats(n_dim, iters); }
-extern "C" int imp_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, int n_mat, int n_dim,
-                                    int head_dim, int iters, float* y, float* saved, void* stream) {
+extern "C" int imp_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, const float* conv_w,
+                                    int heads, int taps, int n_mat, int n_dim, int head_dim, int iters, float* y,
+                                    float* saved, void* stream) {
   if (!mat || !inv_scale || !v || !y) IMP_FAIL(IMP_ERR_ARG, "imp_nystrom_core_fwd: null pointer");
-  return launch_nystrom_core_fwd(mat, inv_scale, v, n_mat, n_dim, head_dim, iters, y, saved, ST(stream));
+  return launch_nystrom_core_fwd(mat, inv_scale, v, conv_w, heads, taps, n_mat, n_dim, head_dim, iters, y, saved, ST(stream));
 }
 extern "C" int imp_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy,
-                                    const float* saved, int n_mat, int n_dim, int head_dim, int iters, float* dmat,
-                                    float* dscale, float* dv, void* stream) {
+                                    const float* saved, const float* conv_w, int heads, int taps, int n_mat, int n_dim,
+                                    int head_dim, int iters, float* dmat, float* dscale, float* dv, float* dconv,
+                                    void* stream) {
   if (!mat || !inv_scale || !v || !dy || !dmat || !dscale || !dv) IMP_FAIL(IMP_ERR_ARG, "imp_nystrom_core_bwd: null pointer");
-  return launch_nystrom_core_bwd(mat, inv_scale, v, dy, saved, n_mat, n_dim, head_dim, iters, dmat, dscale, dv, ST(stream));
+  return launch_nystrom_core_bwd(mat, inv_scale, v, dy, saved, conv_w, heads, taps, n_mat, n_dim, head_dim, iters, dmat,
+                                 dscale, dv, dconv, ST(stream));
 }

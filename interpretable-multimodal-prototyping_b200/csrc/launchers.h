@@ -59,7 +59,8 @@ int launch_lse_merge(const float* part_pooled, const float* part_lse, int B, int
 
 // nystrom.cu
 size_t nystrom_core_saved_floats(int N, int iters);
-int launch_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, int BH, int N, int d, int iters,
-                            float* y, float* zs, cudaStream_t st);
+int launch_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, const float* conv_w, int heads,
+                            int taps, int BH, int N, int d, int iters, float* y, float* zs, cudaStream_t st);
 int launch_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy, const float* zs,
-                            int BH, int N, int d, int iters, float* dmat, float* dscale, float* dv, cudaStream_t st);
+                            const float* conv_w, int heads, int taps, int BH, int N, int d, int iters, float* dmat,
+                            float* dscale, float* dv, float* dconv, cudaStream_t st);

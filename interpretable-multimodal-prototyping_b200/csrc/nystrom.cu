@@ -78,6 +78,9 @@ struct NyParams {
   float* dscale;           // (BH) partial derivatives wrt s
   float* zs;               // (BH, iters + 1, NP * (NP + 1)) the iterates Z_k in the shared-memory layout: written by the
                            // forward (may be null), read by the backward instead of running the iteration again
+  const float* conv_w;     // (heads, taps) depth-wise residual convolution over the tokens (attention.py:129-131), or null
+  float* dconv;            // (BH, taps) per-matrix partial gradients of conv_w        backward only
+  int heads, taps;         // matrix index = slide * heads + head; taps odd (33)
   int N, d, iters;
 };
 
@@ -152,9 +155,16 @@ __global__ void __launch_bounds__(kNyThreads, 2) nystrom_core_fwd_kernel(const N
   mm<false, false, false>(W1, LDV, A, LD, W2, LDV, NP, d, NP, 1.f);        // W1 is free again: Y
   __syncthreads();
   float* dst = p.y + (size_t)blockIdx.x * (N - 1) * d;
+  const float* cw = p.conv_w ? p.conv_w + (size_t)(blockIdx.x % p.heads) * p.taps : nullptr;
+  const int half = p.taps >> 1;
   for (int idx = threadIdx.x; idx < (N - 1) * d; idx += kNyThreads) {
     const int i = idx / d, c = idx - i * d;
-    dst[idx] = W1[(i + 1) * LDV + c];
+    float acc = W1[(i + 1) * LDV + c];
+    if (cw) {                                       // + sum_t w[t] v[i + t - half]: the zero tokens the reference pads in
+      const int t0 = max(0, half - i), t1 = min(p.taps, N - 1 - i + half);      // front act like the conv's own padding
+      for (int t = t0; t < t1; ++t) acc = fmaf(__ldg(cw + t), V1[(i + t - half + 1) * LDV + c], acc);
+    }
+    dst[idx] = acc;
   }
 }
 
@@ -216,9 +226,29 @@ __global__ void __launch_bounds__(kNyThreads, 1) nystrom_core_bwd_kernel(const N
   __syncthreads();
   {
     float* dst = p.dv + (size_t)blockIdx.x * (N - 1) * d;
-    for (int idx = threadIdx.x; idx < (N - 1) * d; idx += kNyThreads) {
+    const float* cw = p.conv_w ? p.conv_w + (size_t)(blockIdx.x % p.heads) * p.taps : nullptr;
+    const int half = p.taps >> 1, n = N - 1;
+    for (int idx = threadIdx.x; idx < n * d; idx += kNyThreads) {
       const int i = idx / d, c = idx - i * d;
-      dst[idx] = W2[(i + 1) * LDV + c];
+      float acc = W2[(i + 1) * LDV + c];
+      if (cw) {                                     // transpose of the convolution: dv[i] += sum_t w[t] dy[i - t + half]
+        const int t0 = max(0, i + half - n + 1), t1 = min(p.taps, i + half + 1);
+        for (int t = t0; t < t1; ++t) acc = fmaf(__ldg(cw + t), dY[(i - t + half + 1) * LDV + c], acc);
+      }
+      dst[idx] = acc;
+    }
+    if (cw) {                                       // dw[t] = sum_{i,c} dy[i][c] v[i + t - half][c], one warp per tap
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      for (int t = warp; t < p.taps; t += kNyThreads / 32) {
+        const int i0 = max(0, half - t), i1 = min(n, n + half - t);
+        float acc = 0.f;
+        for (int idx = i0 * d + lane; idx < i1 * d; idx += 32) {
+          const int i = idx / d, c = idx - i * d;
+          acc = fmaf(dY[(i + 1) * LDV + c], V1[(i + t - half + 1) * LDV + c], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) p.dconv[(size_t)blockIdx.x * p.taps + t] = acc;
+      }
     }
   }
   __syncthreads();                                // the vectors are dead: the scratch matrices may be overwritten
@@ -290,10 +320,19 @@ size_t nystrom_core_saved_floats(int N, int iters) {
   return (size_t)(iters + 1) * NP * (NP + 1);
 }
 
-int launch_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, int BH, int N, int d, int iters,
-                            float* y, float* zs, cudaStream_t st) {
+static int ny_check_conv(const float* conv_w, int heads, int taps, int BH, const char* who) {
+  if (!conv_w) return IMP_OK;
+  if (heads <= 0 || BH % heads) IMP_FAIL(IMP_ERR_ARG, "%s: %d matrices are not a multiple of %d heads", who, BH, heads);
+  if (taps <= 0 || !(taps & 1) || taps > 129) IMP_FAIL(IMP_ERR_ARG, "%s: the residual convolution needs an odd number of taps <= 129 (got %d)", who, taps);
+  return IMP_OK;
+}
+
+int launch_nystrom_core_fwd(const float* mat, const float* inv_scale, const float* v, const float* conv_w, int heads,
+                            int taps, int BH, int N, int d, int iters, float* y, float* zs, cudaStream_t st) {
   { const int rc = ny_check(BH, N, d, iters, "nystrom_core_fwd"); if (rc) return rc; }
+  { const int rc = ny_check_conv(conv_w, heads, taps, BH, "nystrom_core_fwd"); if (rc) return rc; }
   NyParams p{};
+  p.conv_w = conv_w; p.heads = conv_w ? heads : 1; p.taps = conv_w ? taps : 1;
   p.mat = mat; p.inv_scale = inv_scale; p.v = v; p.y = y; p.zs = zs; p.N = N; p.d = d; p.iters = iters;
   const size_t smem = ny_fwd_smem(N, d);
   { const int rc = imp_ensure_smem((const void*)nystrom_core_fwd_kernel, 227 * 1024 - 1024); if (rc) return rc; }
@@ -302,9 +341,13 @@ int launch_nystrom_core_fwd(const float* mat, const float* inv_scale, const floa
 }
 
 int launch_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy, const float* zs,
-                            int BH, int N, int d, int iters, float* dmat, float* dscale, float* dv, cudaStream_t st) {
+                            const float* conv_w, int heads, int taps, int BH, int N, int d, int iters, float* dmat,
+                            float* dscale, float* dv, float* dconv, cudaStream_t st) {
   { const int rc = ny_check(BH, N, d, iters, "nystrom_core_bwd"); if (rc) return rc; }
+  { const int rc = ny_check_conv(conv_w, heads, taps, BH, "nystrom_core_bwd"); if (rc) return rc; }
+  if (conv_w && !dconv) IMP_FAIL(IMP_ERR_ARG, "nystrom_core_bwd: conv_w without dconv");
   NyParams p{};
+  p.conv_w = conv_w; p.dconv = dconv; p.heads = conv_w ? heads : 1; p.taps = conv_w ? taps : 1;
   p.mat = mat; p.inv_scale = inv_scale; p.v = v; p.dy = dy; p.dmat = dmat; p.dscale = dscale; p.dv = dv;
   p.zs = const_cast<float*>(zs);
   p.N = N; p.d = d; p.iters = iters;

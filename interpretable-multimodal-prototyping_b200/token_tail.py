@@ -52,8 +52,10 @@ def iterative_pinv(a: torch.Tensor, iters: int = 6) -> torch.Tensor:
 # matrices (26 GFLOP per layer call at 32 slides -- 26 ms of a 61 ms whole-model step -- become ~0.3 GFLOP), with
 # results identical up to fp32 round-off.
 # ------------------------------------------------------------------------------------------
-def nystrom_short(q, k, v, m: int, iters: int):
-    """q (scaled), k, v (B,H,n,d) with n < m -> the last n rows of A pinv(A) A [0; v]  (B,H,n,d)."""
+def nystrom_short(q, k, v, m: int, iters: int, conv_w=None):
+    """q (scaled), k, v (B,H,n,d) with n < m -> the last n rows of A pinv(A) A [0; v]  (B,H,n,d), plus the depth-wise
+    residual convolution of v over the tokens when ``conv_w`` (H,1,taps,1) is given (attention.py:129-131; the zero
+    tokens the reference pads in front act like the convolution's own zero padding)."""
     n = q.shape[-2]
     p = float(m - n)
     rp = math.sqrt(p)
@@ -70,14 +72,17 @@ def nystrom_short(q, k, v, m: int, iters: int):
     mat = torch.cat([top, torch.cat([rp * cvec, dmat], dim=-1)], dim=-2)          # M(A), (B,H,n+1,n+1)
     if mat.is_cuda and _core_supported(n + 1, v.shape[-1], iters):
         # one kernel per direction instead of ~85 batched GEMMs and ~100 element-wise launches (csrc/nystrom.cu)
-        return _NystromCore.apply(mat, 1.0 / (rs * cs), v, iters)
+        return _NystromCore.apply(mat, 1.0 / (rs * cs), v, iters, None if conv_w is None else conv_w.reshape(conv_w.shape[0], -1))
     eye = torch.eye(n + 1, device=s.device, dtype=s.dtype)
     z = mat.transpose(-1, -2) / (rs * cs)
     for _ in range(iters):
         az = mat @ z
         z = 0.25 * z @ (13 * eye - az @ (15 * eye - az @ (7 * eye - az)))
     v1 = F.pad(v, (0, 0, 1, 0))                                  # coordinates of [0; v]: zero along u
-    return (mat @ (z @ (mat @ v1)))[..., 1:, :]
+    out = (mat @ (z @ (mat @ v1)))[..., 1:, :]
+    if conv_w is not None:
+        out = out + F.conv2d(v, conv_w, padding=(conv_w.shape[2] // 2, 0), groups=conv_w.shape[0])
+    return out
 
 
 def _core_supported(n_dim: int, head_dim: int, iters: int) -> bool:
@@ -92,19 +97,25 @@ class _NystromCore(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, mat, inv_scale, v, iters):
+    def forward(ctx, mat, inv_scale, v, iters, conv_w=None):
         from . import _lib
         mat, v = mat.contiguous(), v.contiguous()
+        heads, taps = (conv_w.shape[0], conv_w.shape[1]) if conv_w is not None else (1, 1)
+        if conv_w is not None:
+            conv_w = conv_w.contiguous()
+            if v.dim() != 4 or v.shape[1] != heads:
+                raise ValueError("v must be (slides, heads, tokens, head_dim) with %d heads" % heads)
         inv_scale = inv_scale.reshape(1).contiguous()
         n_dim, d = mat.shape[-1], v.shape[-1]
         n_mat = mat.numel() // (n_dim * n_dim)
         y = torch.empty_like(v)
         saved = None
-        if any(ctx.needs_input_grad[:3]):                     # the iterates Z_k, so that the backward does not repeat the iteration
+        if any(ctx.needs_input_grad):                         # the iterates Z_k, so that the backward does not repeat the iteration
             saved = torch.empty(n_mat, _lib.query("imp_nystrom_core_saved_floats", n_dim, int(iters)), device=mat.device,
                                 dtype=torch.float32)
-        _lib.call("imp_nystrom_core_fwd", mat, inv_scale, v, n_mat, n_dim, d, int(iters), y, saved, _lib.stream_ptr())
-        ctx.save_for_backward(mat, inv_scale, v, saved)
+        _lib.call("imp_nystrom_core_fwd", mat, inv_scale, v, conv_w, heads, taps, n_mat, n_dim, d, int(iters), y, saved,
+                  _lib.stream_ptr())
+        ctx.save_for_backward(mat, inv_scale, v, saved, conv_w)
         ctx.iters = int(iters)
         return y
 
@@ -112,15 +123,18 @@ class _NystromCore(torch.autograd.Function):
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dy):
         from . import _lib
-        mat, inv_scale, v, saved = ctx.saved_tensors
+        mat, inv_scale, v, saved, conv_w = ctx.saved_tensors
         n_dim, d = mat.shape[-1], v.shape[-1]
         n_mat = mat.numel() // (n_dim * n_dim)
         dy = dy.contiguous().float()
         dmat, dv = torch.empty_like(mat), torch.empty_like(v)
         dscale = torch.empty(n_mat, device=mat.device, dtype=torch.float32)
-        _lib.call("imp_nystrom_core_bwd", mat, inv_scale, v, dy, saved, n_mat, n_dim, d, ctx.iters, dmat, dscale, dv,
-                  _lib.stream_ptr())
-        return dmat, dscale.sum().reshape(()), dv, None
+        heads, taps = (conv_w.shape[0], conv_w.shape[1]) if conv_w is not None else (1, 1)
+        dconv = torch.empty(n_mat, taps, device=mat.device, dtype=torch.float32) if conv_w is not None else None
+        _lib.call("imp_nystrom_core_bwd", mat, inv_scale, v, dy, saved, conv_w, heads, taps, n_mat, n_dim, d, ctx.iters, dmat,
+                  dscale, dv, dconv, _lib.stream_ptr())
+        return (dmat, dscale.sum().reshape(()), dv, None,
+                None if conv_w is None else dconv.view(-1, heads, taps).sum(0))
 
 
 class NystromAttention(nn.Module):
@@ -143,9 +157,7 @@ class NystromAttention(nn.Module):
         if n < m:                                               # every call of this model: reduced block algebra
             qkv = self.to_qkv(x).view(b, n, 3, h, -1).permute(2, 0, 3, 1, 4)
             q, k, v = qkv[0] * self.scale, qkv[1], qkv[2]
-            out = nystrom_short(q, k, v, m, self.pinv_iterations)
-            if self.residual:                                   # zero tokens in front act like the conv's own zero padding
-                out = out + self.res_conv(v)
+            out = nystrom_short(q, k, v, m, self.pinv_iterations, self.res_conv.weight if self.residual else None)
             return self.to_out(out.transpose(1, 2).reshape(b, n, -1))
         return self.forward_dense(x)
 

@@ -73,7 +73,7 @@ def test_nystrom_core_rejects_unsupported_shapes():
     s = torch.ones(1, device="cuda")
     v = torch.zeros(2, 49, 32, device="cuda")
     with pytest.raises(_lib.ImpError):
-        _lib.call("imp_nystrom_core_fwd", mat, s, v, 2, 50, 32, 6, torch.empty_like(v), None, _lib.stream_ptr())
+        _lib.call("imp_nystrom_core_fwd", mat, s, v, None, 1, 1, 2, 50, 32, 6, torch.empty_like(v), None, _lib.stream_ptr())
 
 
 def test_nystrom_backward_with_and_without_kept_iterates():
@@ -86,12 +86,38 @@ def test_nystrom_backward_with_and_without_kept_iterates():
     v, dy = torch.randn(n_mat, n_dim - 1, d, device="cuda"), torch.randn(n_mat, n_dim - 1, d, device="cuda")
     y = torch.empty_like(v)
     saved = torch.empty(n_mat, _lib.query("imp_nystrom_core_saved_floats", n_dim, iters), device="cuda")
-    _lib.call("imp_nystrom_core_fwd", mat, s, v, n_mat, n_dim, d, iters, y, saved, _lib.stream_ptr())
+    w = torch.randn(8, 33, device="cuda") * 0.1                       # residual convolution: 8 heads, 33 taps
+    _lib.call("imp_nystrom_core_fwd", mat, s, v, w, 8, 33, n_mat, n_dim, d, iters, y, saved, _lib.stream_ptr())
     res = []
     for buf in (saved, None):
         dmat, dv, ds = torch.empty_like(mat), torch.empty_like(v), torch.empty(n_mat, device="cuda")
-        _lib.call("imp_nystrom_core_bwd", mat, s, v, dy, buf, n_mat, n_dim, d, iters, dmat, ds, dv, _lib.stream_ptr())
-        res.append((dmat, dv, ds))
+        dw = torch.empty(n_mat, 33, device="cuda")
+        _lib.call("imp_nystrom_core_bwd", mat, s, v, dy, buf, w, 8, 33, n_mat, n_dim, d, iters, dmat, ds, dv, dw, _lib.stream_ptr())
+        res.append((dmat, dv, ds, dw))
     torch.cuda.synchronize()
     for a, b in zip(*res):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n", [5, 20, 38])
+def test_fused_residual_convolution(n, monkeypatch):
+    """nystrom_short with the depth-wise residual convolution inside the kernel against the batched form + F.conv2d:
+    outputs, and gradients into q, k, v and the convolution weight (n < 17, = and > the half-width of the 33 taps)."""
+    from imp_b200 import token_tail as T
+    torch.manual_seed(n)
+    b, h, d, m = 4, 8, 32, 128
+    q = torch.randn(b, h, n, d, device="cuda", dtype=torch.float64) * d ** -0.5
+    k, v = torch.randn(b, h, n, d, device="cuda", dtype=torch.float64), torch.randn(b, h, n, d, device="cuda", dtype=torch.float64)
+    w = torch.randn(h, 1, 33, 1, device="cuda", dtype=torch.float64) * 0.2
+    res = []
+    for use_kernel, dt in ((True, torch.float32), (False, torch.float64)):
+        with monkeypatch.context() as mp:
+            if not use_kernel:
+                mp.setattr(T, "_core_supported", lambda *a: False)
+            args = [t.to(dt).clone().requires_grad_(True) for t in (q, k, v, w)]
+            out = T.nystrom_short(args[0], args[1], args[2], m, 6, args[3])
+            g = torch.autograd.grad((out * torch.linspace(-1, 1, out.numel(), device="cuda", dtype=dt).view_as(out)).sum(), args)
+            res.append((out.detach(), g))
+    assert _rel(res[0][0], res[1][0]) < 1e-4
+    for a, b_, name in zip(res[0][1], res[1][1], "qkvw"):
+        assert _rel(a, b_) < 1e-3, (name, _rel(a, b_))
