@@ -593,7 +593,7 @@ constexpr size_t sweep_smem() {
   return 1024 + kABytes + kBBytes + (size_t)kLStages * (kBN * PtPad * 4 + kBN * 4) + (size_t)PtPad * kBM * 4 + kBM * 4 + 64 + 512;
 }
 
-template <int NQ1, int NQ2, bool LASTPAD, int POLLMASK = 0xF>      // LASTPAD: the last token slot is padding (never wins): skipped
+template <int NQ1, int NQ2, bool LASTPAD>      // LASTPAD: the last token slot is padding (never wins): skipped
 __global__ void __launch_bounds__(kSwThreads, 1)
 modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                         const GramParams p) {
@@ -883,12 +883,10 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     };
     auto tile = [&](auto interior_tag) {
 #pragma unroll 2      // not 4: the fully unrolled tile (21 KB of SASS per variant) stalled on instruction fetch (37.6 -> 35.8 ms); 1 is slower (38.6)
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < 4; ++g) {       // probe points per tile, measured (ms per 32 bags): 1: 35.9 | 2: 33.2 | 4: 32.8 | 6: 33.8 | 8: 34.8
         group4(g, interior_tag);
-        if ((POLLMASK >> g) & 1) {
-          poll(it);
-          __syncwarp();
-        }
+        poll(it);
+        __syncwarp();
       }
     };
     if (interior) tile(std::true_type{}); else tile(std::false_type{});
@@ -1164,12 +1162,12 @@ int run_degrees(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& 
   return IMP_OK;
 }
 
-template <int NQ1, int NQ2, bool LASTPAD = false, int POLLMASK = 0xF>
+template <int NQ1, int NQ2, bool LASTPAD = false>
 int run_sweep(const CUtensorMap& ta, const CUtensorMap& tb, const GramParams& p, dim3 grid, cudaStream_t st) {
   constexpr size_t smem = sweep_smem<NQ1, NQ2>();
   static_assert(smem <= 227 * 1024, "modularity_sweep shared memory");
-  { const int rc_ = imp_ensure_smem((const void*)modularity_sweep_kernel<NQ1, NQ2, LASTPAD, POLLMASK>, smem); if (rc_) return rc_; }
-  IMP_LAUNCH("modularity_sweep", st, modularity_sweep_kernel<NQ1, NQ2, LASTPAD, POLLMASK><<<grid, kSwThreads, smem, st>>>(ta, tb, p));
+  { const int rc_ = imp_ensure_smem((const void*)modularity_sweep_kernel<NQ1, NQ2, LASTPAD>, smem); if (rc_) return rc_; }
+  IMP_LAUNCH("modularity_sweep", st, modularity_sweep_kernel<NQ1, NQ2, LASTPAD><<<grid, kSwThreads, smem, st>>>(ta, tb, p));
   return IMP_OK;
 }
 
@@ -1319,12 +1317,7 @@ int launch_modularity_execute(const bf16* h_local, int local_rows, int row_lo, i
     const dim3 grid(row_blocks, nsplit, B);
 #define IMP_SWEEP(a, b2) rc = run_sweep<a, b2>(ta, tb, gp, grid, st)
     if (nq2 == 0) { if (nq1 == 2) IMP_SWEEP(2, 0); else if (nq1 == 4) IMP_SWEEP(4, 0); else IMP_SWEEP(8, 0); }
-    else if (nq1 == 8 && (P2 & 3)) {                                                       // the 32 + 7 token configuration
-      static const int polls = []() { const char* e = getenv("IMP_SWEEP_POLLS"); return e ? atoi(e) : 4; }();   // tuning switch
-      if (polls == 2) rc = run_sweep<8, 2, true, 0xA>(ta, tb, gp, grid, st);
-      else if (polls == 1) rc = run_sweep<8, 2, true, 0x8>(ta, tb, gp, grid, st);
-      else rc = run_sweep<8, 2, true>(ta, tb, gp, grid, st);
-    }
+    else if (nq1 == 8 && (P2 & 3)) rc = run_sweep<8, 2, true>(ta, tb, gp, grid, st);     // the 32 + 7 token configuration
     else { if (nq1 == 2) IMP_SWEEP(2, 2); else if (nq1 == 4) IMP_SWEEP(4, 2); else IMP_SWEEP(8, 2); }
 #undef IMP_SWEEP
     if (rc) return rc;
