@@ -584,13 +584,19 @@ constexpr int kSwThreads = kSwWarps * 32;           // 512
 #ifdef IMP_SWEEP_TRACE
 __device__ unsigned long long g_sweep_trace[16 * 8];   // debug counters (profiles/r01_sweep_iterations.md)
 #endif
-constexpr int kTBufs = 8;                           // ring slots: TMEM accumulator of 64 columns + L/degree tile (4 slots: 33.4 ms, 8: 32.9)
+#ifndef IMP_SWEEP_BSTAGES
+#define IMP_SWEEP_BSTAGES 2
+#endif
+constexpr int kBStages = IMP_SWEEP_BSTAGES;         // B boxes in flight: with one, the production of a tile is a serial chain
+                                                    // MMA retire -> probe -> TMA load -> probe -> MMA issue of ~4 us against 4.6 us of pair work
+constexpr int kTBufs = kBStages == 1 ? 8 : 6;       // ring slots: TMEM accumulator of 64 columns + L/degree tile (4 slots: 33.4 ms, 8: 32.9)
 constexpr int kLStages = kTBufs;
+constexpr int kSwTmemCols = kTBufs * kBN <= 256 ? 256 : 512;   // allocations are powers of two
 
 template <int NQ1, int NQ2>
 constexpr size_t sweep_smem() {
   constexpr int PtPad = 4 * (NQ1 + NQ2);
-  return 1024 + kABytes + kBBytes + (size_t)kLStages * (kBN * PtPad * 4 + kBN * 4) + (size_t)PtPad * kBM * 4 + kBM * 4 + 64 + 512;
+  return 1024 + kABytes + kBStages * kBBytes + (size_t)kLStages * (kBN * PtPad * 4 + kBN * 4) + (size_t)PtPad * kBM * 4 + kBM * 4 + 64 + 512;
 }
 
 template <int NQ1, int NQ2, bool LASTPAD>      // LASTPAD: the last token slot is padding (never wins): skipped
@@ -605,14 +611,14 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   uint8_t* smem = align1024(smem_raw);
   uint8_t* s_a = smem;
   uint8_t* s_b = s_a + kABytes;
-  uint8_t* s_l = s_b + kBBytes;
+  uint8_t* s_l = s_b + kBStages * kBBytes;
   int* s_T = reinterpret_cast<int*>(s_l + kLStages * kLStage);           // [PtPad][128] fixed point, one row per patch
   float* s_invS = reinterpret_cast<float*>(s_T + (size_t)PtPad * kBM);   // [128] 1 / scale of the row
   float* s_dm = s_invS + kBM;                                            // [16] per-warp maxima of the degrees
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_dm + 16);
-  uint64_t* bfull = bars;                 // TMA -> MMA
-  uint64_t* bempty = bars + 1;            // MMA commit -> TMA
-  uint64_t* full = bars + 2;              // [kTBufs] ring slot filled: L/degree bytes landed AND the MMAs retired
+  uint64_t* bfull = bars;                 // [kBStages] TMA -> MMA
+  uint64_t* bempty = bars + kBStages;     // [kBStages] MMA commit -> TMA
+  uint64_t* full = bars + 2 * kBStages;   // [kTBufs] ring slot filled: L/degree bytes landed AND the MMAs retired
   uint64_t* empty = full + kTBufs;        // [kTBufs] ring slot consumed by all 16 warps
   uint64_t* afull = empty + kTBufs;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
@@ -634,7 +640,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
-    mbar_init(bfull, 1); mbar_init(bempty, 1);
+    for (int i = 0; i < kBStages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
     for (int i = 0; i < kTBufs; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], kSwWarps); }   // 2 = expect_tx arrive + commit
     mbar_init(afull, 1);
     *s_mcnt = 0;
@@ -642,7 +648,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     s_desc[1] = umma_desc_sw128(smem_u32(s_b), 0, 1024);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, kTBufs * kBN);
+  if (warp == 0) tmem_alloc(tmem_slot, kSwTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -664,9 +670,11 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   int b_pend = -1;                                     // tile whose step 2 is pending, or -1
   auto issue_b = [&](int n) {                          // B box of tile n
     if (elect_one()) {
-      mbar_arrive_expect_tx(bfull, kBBytes);
+      const int bs = n % kBStages;
+      mbar_arrive_expect_tx(&bfull[bs], kBBytes);
 #pragma unroll
-      for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_b + bx * (kBN * 128), &tm_b, bfull, bx * 64, (t0 + n) * kBN);
+      for (int bx = 0; bx < 4; ++bx)
+        tma_load_2d(s_b + bs * kBBytes + bx * (kBN * 128), &tm_b, &bfull[bs], bx * 64, (t0 + n) * kBN);
     }
     __syncwarp();
   };
@@ -682,27 +690,28 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
       // base descriptors come from shared memory: computed here from the (loop-invariant) buffer addresses, ptxas
       // hoists the 32 additions below out of this block into every warp's tile loop (~40 instructions per tile)
-      const uint64_t ad0 = s_desc[0], bd0 = s_desc[1];
+      const uint64_t ad0 = s_desc[0], bd0 = s_desc[1] + (uint64_t)((m_next % kBStages) * (kBBytes >> 4));
       const uint32_t tacc = tmem_base + slot * kBN;
 #pragma unroll
       for (int k = 0; k < kD / 16; ++k)      // descriptor start addresses advance in 16-byte units
         umma_f16(tacc, ad0 + (uint64_t)(((k >> 2) * (kBM * 128) + (k & 3) * 32) >> 4),
                  bd0 + (uint64_t)(((k >> 2) * (kBN * 128) + (k & 3) * 32) >> 4), idesc, k != 0);
-      umma_commit(bempty);
+      umma_commit(&bempty[m_next % kBStages]);
       umma_commit(&full[slot]);
       *s_mcnt = m_next + 1;
     }
-    b_pend = (m_next + 1 < ntiles) ? m_next : -1;
+    b_pend = (m_next + kBStages < ntiles) ? m_next : -1;     // the owner of tile n loads B box n + kBStages into the stage n frees
     m_next += kSwWarps;
     __syncwarp();
   };
   // non-blocking (every lane probes and the vote keeps the answer, and with it m_next / b_pend, warp-uniform)
   auto poll = [&](int it) {
     if (b_pend >= 0) {
-      if (__all_sync(0xffffffffu, mbar_test(bempty, b_pend & 1))) { issue_b(b_pend + 1); b_pend = -1; }
+      if (__all_sync(0xffffffffu, mbar_test(&bempty[b_pend % kBStages], (b_pend / kBStages) & 1))) { issue_b(b_pend + kBStages); b_pend = -1; }
     } else if (m_next < ntiles && m_next - it <= kTBufs) {      // its ring slot can be free at the earliest now
       const uint32_t par = ((m_next / kTBufs) & 1) ^ 1;
-      const bool open = (*s_mcnt == m_next) && mbar_test(bfull, m_next & 1) && mbar_test(&empty[m_next % kTBufs], par);
+      const bool open = (*s_mcnt == m_next) && mbar_test(&bfull[m_next % kBStages], (m_next / kBStages) & 1) &&
+                        mbar_test(&empty[m_next % kTBufs], par);
       if (__all_sync(0xffffffffu, open)) step1();
     }
   };
@@ -710,15 +719,15 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   // older tiles, which every warp that reached `it` has passed, and on steps their owners complete here.
   auto ensure = [&](int it) {
     if (b_pend >= 0 && b_pend < it) {
-      mbar_wait_idle(bempty, b_pend & 1, 2000u);
+      mbar_wait_idle(&bempty[b_pend % kBStages], (b_pend / kBStages) & 1, 2000u);
       __syncwarp();
-      issue_b(b_pend + 1);
+      issue_b(b_pend + kBStages);
       b_pend = -1;
     }
     if (m_next <= it) {
       const uint32_t par = ((m_next / kTBufs) & 1) ^ 1;
       while (*s_mcnt != m_next) {}
-      mbar_wait_idle(bfull, m_next & 1, 2000u);
+      mbar_wait_idle(&bfull[m_next % kBStages], (m_next / kBStages) & 1, 2000u);
       mbar_wait_idle(&empty[m_next % kTBufs], par, 2000u);
       __syncwarp();
       step1();
@@ -731,7 +740,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
       for (int bx = 0; bx < 4; ++bx) tma_load_2d(s_a + bx * (kBM * 128), &tm_a, afull, bx * 64, i0);
     }
     __syncwarp();
-    issue_b(0);
+    for (int n = 0; n < kBStages && n < ntiles; ++n) issue_b(n);
   }
   mbar_wait(afull, 0);                                   // every warp issues MMAs that read the A tile
 
@@ -929,7 +938,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTBufs * kBN);
+    tmem_dealloc(tmem_base, kSwTmemCols);
   }
 }
 
