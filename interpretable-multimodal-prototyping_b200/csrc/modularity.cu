@@ -570,9 +570,10 @@ modularity_degrees_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
 //   the 64 columns, four at a time), 128 registers per thread (a 17th warp would cap every thread at 96).
 //   No dedicated producer / MMA warps: the pair work of a tile takes microseconds, so the sweep warps drive the
 //   asynchronous machinery themselves, in rotation, with non-blocking mbarrier probes (five probe points per
-//   tile): bulk copies of the L/degree tiles and the tcgen05 MMA 128x64x256 into a ring of eight slots (TMEM
-//   accumulator + L tile: all 512 TMEM columns), up to seven tiles ahead, and the TMA load of the B box (1 stage: it is free again as
-//   soon as its MMA retires).
+//   tile): bulk copies of the L/degree tiles and the tcgen05 MMA 128x64x256 into a ring of six slots (TMEM
+//   accumulator + L tile), up to five tiles ahead, and the TMA loads of the B boxes (two stages: with one, producing a
+//   tile was the serial chain MMA retire -> probe -> TMA load -> probe -> MMA issue, ~4 us against 4.6 us of pair work
+//   per tile, and paced the kernel: 32.8 -> 31.2 ms per 32 bags).
 //   Per four columns a thread runs
 //     - the (min,+) contraction over tokens: per token pair 2 broadcast 128-bit loads of L (token-major tile),
 //       4 FADD2 (two columns each, row operand broadcast) and 4 FMNMX3 (one per column chain);
@@ -589,7 +590,8 @@ __device__ unsigned long long g_sweep_trace[16 * 8];   // debug counters (profil
 #endif
 constexpr int kBStages = IMP_SWEEP_BSTAGES;         // B boxes in flight: with one, the production of a tile is a serial chain
                                                     // MMA retire -> probe -> TMA load -> probe -> MMA issue of ~4 us against 4.6 us of pair work
-constexpr int kTBufs = kBStages == 1 ? 8 : 6;       // ring slots: TMEM accumulator of 64 columns + L/degree tile (4 slots: 33.4 ms, 8: 32.9)
+constexpr int kTBufs = kBStages == 1 ? 8 : 6;       // ring slots: TMEM accumulator of 64 columns + L/degree tile.  One B stage: 4 slots 33.4 ms,
+                                                    // 8 slots 32.9; two B stages: 6 slots 31.24, 7 slots 31.33 (and 1-4 probe points per tile within 0.4 ms)
 constexpr int kLStages = kTBufs;
 constexpr int kSwTmemCols = kTBufs * kBN <= 256 ? 256 : 512;   // allocations are powers of two
 
@@ -655,17 +657,17 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   // Producer work rotates over the 16 warps: warp n % 16 owns tile n and, from inside its own sweep, at non-blocking
   // probe points (five per tile), performs
-  //   step 1 (gates: tiles < n issued, B box n landed, ring slot n % 8 released by all 16 warps):
-  //           bulk copies of the L / degree tile n, the 16 tcgen05 MMAs of tile n, commits to bempty and full;
-  //   step 2 (gate: the MMAs of tile n have retired = bempty): TMA load of B box n + 1 (single stage).
+  //   step 1 (gates: tiles < n issued, B box n landed, ring slot n % kTBufs released by all 16 warps):
+  //           bulk copies of the L / degree tile n, the 16 tcgen05 MMAs of tile n, commits to bempty[n % 2] and full;
+  //   step 2 (gate: the MMAs of tile n have retired = bempty[n % 2]): TMA load of B box n + 2 into the stage n frees.
   // Every step runs on a whole, converged warp and the asynchronous instructions on the lane elect.sync picks:
   // inside an elect-guarded block ptxas keeps descriptors and barrier addresses in uniform registers (~45
   // instructions for the 16 MMAs); behind a `lane == 0` test it wraps every UTCHMMA / UTMALDG in a per-lane
   // waterfall loop (~220).  Pinned roles (MMA on warp 13, B on 14, L on 15) made those warps the slowest of the
   // CTA - each mbarrier probe is a round trip through the busy shared-memory pipe, and the MMA issue stalls its
   // warp - and the other warps then sat at the accumulator barrier for 15% of the kernel (IMP_SWEEP_TRACE).
-  // s_mcnt = number of tiles issued: bfull is one barrier whose phase flips every tile, so it may only be probed
-  // for tile n once tile n-1 has been issued (before that, parity n&1 still reads as phase n-2).
+  // s_mcnt = number of tiles issued: a bfull barrier flips its phase every kBStages tiles, so it may only be probed
+  // for tile n once tile n-1 has been issued (before that, its parity could still read as an older phase).
   int m_next = warp;                                   // next tile this warp owns (step 1 pending)
   int b_pend = -1;                                     // tile whose step 2 is pending, or -1
   auto issue_b = [&](int n) {                          // B box of tile n
@@ -892,7 +894,7 @@ modularity_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     };
     auto tile = [&](auto interior_tag) {
 #pragma unroll 2      // not 4: the fully unrolled tile (21 KB of SASS per variant) stalled on instruction fetch (37.6 -> 35.8 ms); 1 is slower (38.6)
-      for (int g = 0; g < 4; ++g) {       // probe points per tile, measured (ms per 32 bags): 1: 35.9 | 2: 33.2 | 4: 32.8 | 6: 33.8 | 8: 34.8
+      for (int g = 0; g < 4; ++g) {       // probe points per tile, measured with ONE B stage (ms per 32 bags): 1: 35.9 | 2: 33.2 | 4: 32.8 | 6: 33.8 | 8: 34.8
         group4(g, interior_tag);
         poll(it);
         __syncwarp();
