@@ -431,6 +431,50 @@ def giant_measure(dev, rank, world, P, steps, warmup, with_single):
             return c.detach()
         return step
 
+    def make_loss(xs, rows, grp, row0):
+        cu = torch.tensor([0, rows], dtype=torch.int32, device=dev)
+        seed = net._seed() if net.dropout > 0 else 0          # a constant inside a graph; GraphedStep's seed word varies it
+
+        def loss_fn():
+            c, h = ops.proto_fusion(xs, cu, max(1, rows), net.p_proto, net.path_net[0].weight, net.path_net[0].bias, blocks,
+                                    p_drop=net.dropout, seed=seed, shard_group=grp)
+            loss = (c * cot).sum()
+            if grp is not None:
+                return loss + MOD.modularity_terms_sharded(h, row0, n, c, group=grp)[0, 0]
+            return loss + MOD.modularity_terms(h, cu, rows, c)[0, 0]
+        return loss_fn
+
+    graph_check = []                                              # |graph loss - eager loss| / |eager loss| per captured step
+
+    def time_graph(loss_fn, sync_group):
+        """The same step replayed from ONE CUDA graph (collectives captured with it): no launch gaps between the ~160
+        small launches and 12 collectives of a step.  Returns ms per step, or raises."""
+        from imp_b200 import step as S
+        with torch.no_grad():
+            eager_loss = float(loss_fn())                         # dropout is off when this is compared (with_single)
+        gs = S.GraphedStep(None).capture_fn(loss_fn, params, dev)
+        try:
+            for _ in range(max(1, warmup)):
+                out = gs.replay()
+            torch.cuda.synchronize()
+            graph_check.append(abs(float(out) - eager_loss) / max(abs(eager_loss), 1e-30))
+            if sync_group:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                gs.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if sync_group:
+                tms = torch.tensor([ms], device=dev)
+                dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+                ms = float(tms.item())
+            return ms / steps
+        finally:
+            gs.close()
+
     def time_it(step, sync_group):
         for _ in range(max(1, warmup)):
             c = step()
@@ -452,6 +496,17 @@ def giant_measure(dev, rank, world, P, steps, warmup, with_single):
         return ms / steps, c, _lib.launch_count() - l0
 
     ms_n, c_n, launches = time_it(make_step(x, b - a, group, a), world > 1)
+    ms_graph = graph_err = None
+    if world > 1 and os.environ.get("IMP_GIANT_GRAPH", "1") != "0":
+        ok = torch.ones(1, device=dev)
+        try:
+            ms_graph = time_graph(make_loss(x, b - a, group, a), True)
+        except Exception as exc:                                  # every rank must agree on whether the number exists
+            graph_err = "%s: %s" % (type(exc).__name__, str(exc)[:160])
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0:
+            ms_graph = None
     agree = 0.0
     if world > 1:
         cs = [torch.empty_like(c_n) for _ in range(world)]
@@ -467,6 +522,17 @@ def giant_measure(dev, rank, world, P, steps, warmup, with_single):
             ms_1, c_1, _ = time_it(make_step(xall, n, None, 0), False)
             rec["ms_per_step_1gpu"] = ms_1
             rec["strong_scaling_speedup"] = ms_1 / ms_n
+            if ms_graph is not None:
+                try:
+                    ms_1g = time_graph(make_loss(xall, n, None, 0), False)
+                    rec.update({"ms_per_step_sharded_graph": ms_graph, "ms_per_step_1gpu_graph": ms_1g,
+                                "strong_scaling_speedup_graph": ms_1g / ms_graph,
+                                "graph": "the per-rank step incl. its NCCL collectives replayed from one CUDA graph, both arms",
+                                "graph_vs_eager_loss_rel_diff": max(graph_check) if not net.dropout else None})
+                except Exception as exc:
+                    rec["graph_error"] = "1-GPU arm: %s: %s" % (type(exc).__name__, str(exc)[:160])
+            elif graph_err:
+                rec["graph_error"] = graph_err
             rec["token_max_abs_diff_sharded_vs_1gpu"] = float((c_1 - c_n).abs().max().item())
             rec["token_rel_err_sharded_vs_1gpu"] = float(((c_1 - c_n).norm() / c_1.norm()).item())
     if world > 1:

@@ -167,6 +167,17 @@ def modularity(h: torch.Tensor, cu_seqlens: torch.Tensor, max_len: int, chat: to
 
 
 _shard_cache = {}
+_cu_cache = {}
+
+
+def _one_bag_cu(total_rows: int, device) -> torch.Tensor:
+    """cu_seqlens [0, total_rows] of a single bag, created once per (size, device): a host->device copy per step would
+    also be illegal inside a CUDA-graph capture."""
+    key = (total_rows, device)
+    cu = _cu_cache.get(key)
+    if cu is None:
+        cu = _cu_cache[key] = torch.tensor([0, total_rows], dtype=torch.int32, device=device)
+    return cu
 
 
 def _cached(name: str, nbytes: int, device) -> torch.Tensor:
@@ -221,7 +232,7 @@ def modularity_sharded(h_local: torch.Tensor, row_offset: int, total_rows: int, 
     per_rows = windows[0][1] - windows[0][0]                      # rows of a full shard: a multiple of 64
     nbytes = _lib.query("imp_modularity_workspace_bytes", total_rows, 1, n_tok1, n_tok2)
     ws = _cached("modularity_ws", nbytes, dev)
-    cu = torch.tensor([0, total_rows], dtype=torch.int32, device=dev)
+    cu = _one_bag_cu(int(total_rows), dev)
     offs, sizes = (ctypes.c_size_t * 4)(), (ctypes.c_size_t * 4)()
     _lib.call("imp_modularity_sections", total_rows, 1, n_tok1, n_tok2, offs, sizes)
     _lib.call("imp_modularity_prepare", h_local, local_rows, int(row_offset), int(total_rows), cu, 1, chat, int(n_tok1),
