@@ -2,7 +2,8 @@
 dq~/dW1) reproduces the single-GPU tokens and gradients; (b) slide-parallel gradient all-reduce equals
 the single-GPU gradients over all slides; (c) the modularity loss of one bag sharded by rows over the ranks
 (all-gather of xh / assignments, all-reduce of the partial traces and token gradients) equals the single-GPU
-loss and gradients.  Skipped with fewer than 2 GPUs."""
+loss and gradients; (d) the sharded step with its collectives captured in one CUDA graph equals the eager step.
+Skipped with fewer than 2 GPUs."""
 import os
 import sys
 
@@ -85,7 +86,31 @@ def _worker(rank, world, port, q):
         t_full = MOD.modularity_terms(hm, cu_m, nmod, cp_f, co_f)
         (t_full[0, 0] + 2.0 * t_full[0, 1]).backward()
         err_m = max(((t_sh - t_full).abs() / (t_full.abs() + 1e-6)).max().item(), rel(cp_s.grad, cp_f.grad), rel(co_s.grad, co_f.grad))
-        q.put((rank, err_c, err_g, err_dp, err_m))
+        # (d) the sharded training step (pooling + modularity, collectives included) replayed from ONE CUDA graph equals
+        #     the eager step
+        leaves = torch.nn.ParameterDict({k.replace(".", "_"): torch.nn.Parameter(v.clone().to(dev)) for k, v in params.items()})
+        L = {k: leaves[k.replace(".", "_")] for k in params}
+        xs = bag[a:b].to(dev).contiguous()
+        cu_s = torch.tensor([0, b - a], dtype=torch.int32, device=dev)
+        blocks_g = [block_tensors(L, 0), block_tensors(L, 1)]
+
+        def loss_fn():
+            c, h = ops.proto_fusion(xs, cu_s, max(1, b - a), p_proto, L["path_net.0.weight"], L["path_net.0.bias"], blocks_g,
+                                    shard_group=dist.group.WORLD)
+            return (c * cot).sum() + MOD.modularity_terms_sharded(h, a, npatch, c, group=dist.group.WORLD)[0, 0]
+
+        plist = list(leaves.parameters())
+        loss_e = loss_fn()
+        loss_e.backward()
+        ref = {k: v.grad.clone() for k, v in leaves.items() if v.grad is not None}
+        loss_e = float(loss_e)
+        gs = S.GraphedStep(None).capture_fn(loss_fn, plist, dev)
+        for _ in range(2):
+            loss_g = gs.replay()
+        torch.cuda.synchronize()
+        err_graph = max([abs(float(loss_g) - loss_e) / abs(loss_e)] + [rel(leaves[k].grad, ref[k]) for k in ref])
+        gs.close()
+        q.put((rank, err_c, err_g, err_dp, err_m, err_graph))
     finally:
         dist.destroy_process_group()
 
@@ -104,8 +129,9 @@ def test_two_gpu_sharded_bag_and_slide_parallel():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, err_c, err_g, err_dp, err_m in res:
+    for rank, err_c, err_g, err_dp, err_m, err_graph in res:
         assert err_c < 2e-4, (rank, err_c)          # same kernels, different split of the softmax
         assert err_g < 2e-3, (rank, err_g)
         assert err_dp < 2e-3, (rank, err_dp)
         assert err_m < 5e-4, (rank, err_m)          # same kernels, row blocks split over the ranks
+        assert err_graph < 1e-3, (rank, err_graph)  # same launches from a graph; fp32 atomics land in another order
