@@ -280,7 +280,8 @@ def drop_in_model_step(dev, x, cu, omic, B, N, P):
         ms_eager, loss = timeit(step)
         rec = {"unit": "bags/s", "bags_per_step": B, "loss": loss, "eager": {"value": B * 1e3 / ms_eager, "ms_per_step": ms_eager},
                "what": "build_model('umeml_gan', cfg) -> model(batch) 7-tuple -> NLL + KD + modularity -> backward; token tail in "
-                       "batched torch (fp32); importance rows kept on the device (IMPORTANCE_LOG='defer') and appended afterwards"}
+                       "batched torch (fp32) with the Nystrom attention core in csrc/nystrom.cu; importance rows kept on the device "
+                       "(IMPORTANCE_LOG='defer') and appended afterwards"}
         try:
             from imp_b200 import step as S
 
