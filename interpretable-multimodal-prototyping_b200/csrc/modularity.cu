@@ -233,20 +233,35 @@ modularity_prep_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const PrepPa
     const int sa = max(bag_lo, r0), sb = min(__ldg(p.cu + b + 1), tile_end);
     if (sa >= sb) continue;
     __syncthreads();                               // the previous bag's MMAs have been consumed (epilogue below ends with the TMEM reads)
-    for (int i = threadIdx.x; i < PTPAD * 64; i += kPtThreads) {
-      const int slot = i >> 6, c = (i & 63) << 2;
-      int src = -1;
-      if (slot < p.P1) src = slot;
-      else if (slot >= p.P1pad && slot - p.P1pad < p.P2) src = p.P1 + slot - p.P1pad;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (src >= 0) v = __ldg(reinterpret_cast<const float4*>(p.chat + ((size_t)b * Pt + src) * kD + c));
-      const uint32_t h01 = pack_bf16x2(v.x, v.y), h23 = pack_bf16x2(v.z, v.w);
-      const uint32_t l01 = pack_bf16x2(v.x - bf16lo(h01), v.y - bf16hi(h01)), l23 = pack_bf16x2(v.z - bf16lo(h23), v.w - bf16hi(h23));
-      const uint32_t boxo = (uint32_t)((c >> 6) * (NB2 * 128));
-      const uint32_t swz = (uint32_t)((c & 7) << 1);
-      const int rh = slot, rl = PTPAD + slot;
-      *reinterpret_cast<uint2*>(s_c + boxo + rh * 128 + ((((c & 63) >> 3) ^ (rh & 7)) << 4) + swz) = make_uint2(h01, h23);
-      *reinterpret_cast<uint2*>(s_c + boxo + rl * 128 + ((((c & 63) >> 3) ^ (rl & 7)) << 4) + swz) = make_uint2(l01, l23);
+    // four token rows in flight per thread: one float4 at a time left every CTA waiting 16 x an L2 round trip here
+    // (a quarter of the kernel's stall samples)
+    for (int i0 = threadIdx.x; i0 < PTPAD * 64; i0 += 4 * kPtThreads) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kPtThreads;
+        const int slot = i >> 6, c = (i & 63) << 2;
+        int src = -1;
+        if (i < PTPAD * 64) {
+          if (slot < p.P1) src = slot;
+          else if (slot >= p.P1pad && slot - p.P1pad < p.P2) src = p.P1 + slot - p.P1pad;
+        }
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(p.chat + ((size_t)b * Pt + src) * kD + c));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kPtThreads;
+        if (i >= PTPAD * 64) break;
+        const int slot = i >> 6, c = (i & 63) << 2;
+        const uint32_t h01 = pack_bf16x2(v[u].x, v[u].y), h23 = pack_bf16x2(v[u].z, v[u].w);
+        const uint32_t l01 = pack_bf16x2(v[u].x - bf16lo(h01), v[u].y - bf16hi(h01)), l23 = pack_bf16x2(v[u].z - bf16lo(h23), v[u].w - bf16hi(h23));
+        const uint32_t boxo = (uint32_t)((c >> 6) * (NB2 * 128));
+        const uint32_t swz = (uint32_t)((c & 7) << 1);
+        const int rh = slot, rl = PTPAD + slot;
+        *reinterpret_cast<uint2*>(s_c + boxo + rh * 128 + ((((c & 63) >> 3) ^ (rh & 7)) << 4) + swz) = make_uint2(h01, h23);
+        *reinterpret_cast<uint2*>(s_c + boxo + rl * 128 + ((((c & 63) >> 3) ^ (rl & 7)) << 4) + swz) = make_uint2(l01, l23);
+      }
     }
     fence_proxy_async_smem();
     tc_fence_before();
