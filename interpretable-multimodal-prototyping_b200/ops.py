@@ -12,7 +12,6 @@ All N-scaling work runs in the CUDA kernels behind ``kernels``; the P x 256 toke
 """
 from __future__ import annotations
 
-import math
 from typing import List, Optional, Sequence, Tuple
 
 import torch
