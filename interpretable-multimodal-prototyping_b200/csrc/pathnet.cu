@@ -39,7 +39,6 @@ struct FwdParams {
   uint32_t drop_thresh;   // keep element iff (16 hash bits) >= drop_thresh = round(65536 p); 0 => no dropout
   uint32_t seed;
   const uint32_t* seed_offset;   // device word XOR-ed into the seed, or null
-  int debug;              // ABLATION (IMP_PATHNET_DEBUG): 1 no epilogue math/stores, 2 no stores, 4 no MMAs
 };
 
 template <int kXStages, int kWStages>
@@ -91,10 +90,6 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           const int xs = xi % kXStages;
           if (!mbar_test(&xempty[xs], ((xi / kXStages) & 1) ^ 1)) break;
           const int tile = (int)blockIdx.x + (xi / kblocks) * (int)gridDim.x, kb = xi % kblocks;
-          if (p.debug & 8) {                        // EXPERIMENT: pull the same k-block of the tile two rounds ahead into L2
-            const int tp = tile + 2 * (int)gridDim.x;
-            if (tp < p.num_tiles) tma_prefetch_2d(&tm_x, kb * kBK, tp * kBM);
-          }
           mbar_arrive_expect_tx(&xfull[xs], kStageBytesA);
           tma_load_2d(x_base + (size_t)xs * kStageBytesA, &tm_x, &xfull[xs], kb * kBK, tile * kBM);
           ++xi;
@@ -203,185 +198,6 @@ pathnet_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   if (warp == kEpiWarps + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// CTA-pair forward (kdim = 512): tcgen05 cta_group::2, M = 256 rows across two SMs, W1 RESIDENT.
-//   The streaming kernel above is bound by the bytes delivered to each SM: 128 KB of x and 256 KB of W1 per tile
-//   (DESIGN.md section 5).  In a pair each CTA supplies HALF of the B operand (128 of the 256 output columns), so a
-//   CTA holds its 128 KB half of W1 in shared memory for its whole life and only x (16 KB per k-block) streams: one
-//   third of the bytes per SM, x delivered once.  Rank 0 (the leader) issues every MMA; both CTAs run a TMA producer
-//   (own x tile, own half of W1) whose complete_tx lands on the LEADER's full barriers; MMA completion is committed
-//   to both CTAs' barriers by multicast; the peer's epilogue warps release the accumulator on the leader's barrier.
-// ------------------------------------------------------------------------------------------
-constexpr int kPairK = 512;
-constexpr int kPairKB = kPairK / kBK;                       // 8 resident k-blocks of W1
-constexpr int kPairXStages = 3;                             // x stages of TWO k-blocks: 256 contiguous bytes per row and request burst
-constexpr int kPairKPS = 2;                                 // k-blocks per x stage
-constexpr uint32_t kPairXStage = kPairKPS * kStageBytesA;   // 32 KB
-constexpr uint32_t kPairWBox = 128 * kBK * 2;               // 16 KB: [128 output columns][64 k]
-constexpr size_t kPairSmem = 1024 + (size_t)kPairKB * kPairWBox + (size_t)kPairXStages * kPairXStage + 256 * 4 + 512;
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
-pathnet_fwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                        const FwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* w_base = smem;                                          // identical offsets in both CTAs
-  uint8_t* x_base = smem + (size_t)kPairKB * kPairWBox;
-  float* s_bias = reinterpret_cast<float*>(x_base + (size_t)kPairXStages * kPairXStage);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
-  uint64_t* xfull = bars;                          // [kPairXStages] used in the leader: x boxes of BOTH CTAs landed
-  uint64_t* xempty = xfull + kPairXStages;         // [kPairXStages] in each CTA: the pair's MMAs on the stage retired
-  uint64_t* wfull = xempty + kPairXStages;         // [kPairKB]      used in the leader: both halves of a W1 k-block landed
-  uint64_t* tfull = wfull + kPairKB;               // [2] in each CTA: accumulator ready
-  uint64_t* tempty = tfull + 2;                    // [2] used in the leader: both CTAs' epilogues have read it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, npairs_grid = gridDim.x >> 1;
-  const int num_pairs = (p.num_tiles + 1) >> 1;
-  const uint32_t seed = p.seed ^ (p.seed_offset ? __ldg(p.seed_offset) : 0u);
-
-  if (threadIdx.x < 256) s_bias[threadIdx.x] = p.bias[threadIdx.x];
-  if (warp == kEpiWarps && lane == 0) {
-    tma_prefetch_desc(&tm_x);
-    tma_prefetch_desc(&tm_w);
-    for (int i = 0; i < kPairXStages; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
-    for (int i = 0; i < kPairKB; ++i) mbar_init(&wfull[i], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * kEpiWarps); }
-    mbar_fence_init();
-  }
-  if (warp == kEpiWarps + 1) tmem_alloc_pair(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                              // both CTAs' barriers exist before anything remote touches them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == kEpiWarps) {
-    // ------------------------------ TMA producer (both CTAs) ------------------------------
-    if (lane == 0) {
-      int n = 0;                                   // x stages issued so far
-      for (int t = pair; t < num_pairs; t += npairs_grid) {
-        const int tile = 2 * t + (int)rank;        // past the last tile: the boxes are zero-filled, the epilogue skips the rows
-        for (int sb = 0; sb < kPairKB / kPairKPS; ++sb, ++n) {
-          const int xs = n % kPairXStages;
-          mbar_wait(&xempty[xs], ((n / kPairXStages) & 1) ^ 1);
-          if (rank == 0) mbar_arrive_expect_tx(&xfull[xs], 2 * kPairXStage);
-          const uint32_t bar = cluster_map(&xfull[xs], 0);
-#pragma unroll
-          for (int j = 0; j < kPairKPS; ++j)
-            tma_load_2d_pair(x_base + (size_t)xs * kPairXStage + j * kStageBytesA, &tm_x, bar, (sb * kPairKPS + j) * kBK, tile * kBM);
-          if (n < kPairKB / kPairKPS) {            // this CTA's half of W1, behind the first x boxes
-#pragma unroll
-            for (int j = 0; j < kPairKPS; ++j) {
-              const int kb = n * kPairKPS + j;
-              if (rank == 0) mbar_arrive_expect_tx(&wfull[kb], 2 * kPairWBox);
-              tma_load_2d_pair(w_base + (size_t)kb * kPairWBox, &tm_w, cluster_map(&wfull[kb], 0), kb * kBK, (int)rank * 128);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == kEpiWarps + 1) {
-    // ------------------------------ MMA issuer (leader only) ------------------------------
-    if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBM, kD, 0, 0);
-      int it = 0, n = 0;
-      for (int t = pair; t < num_pairs; t += npairs_grid, ++it) {
-        const int acc = it & 1;
-        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kD;
-        for (int sb = 0; sb < kPairKB / kPairKPS; ++sb, ++n) {
-          const int xs = n % kPairXStages;
-          mbar_wait(&xfull[xs], (n / kPairXStages) & 1);
-#pragma unroll
-          for (int j = 0; j < kPairKPS; ++j) {
-            const int kb = sb * kPairKPS + j;
-            if (it == 0) mbar_wait(&wfull[kb], 0);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(x_base + (size_t)xs * kPairXStage + j * kStageBytesA);
-            const uint32_t sbw = smem_u32(w_base + (size_t)kb * kPairWBox);
-            if (!(p.debug & 4)) {
-#pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              uint64_t ad = umma_desc_sw128(sa + k * 32, 0, 1024);
-              uint64_t bd = umma_desc_sw128(sbw + k * 32, 0, 1024);
-              umma_f16_pair(d_tmem, ad, bd, idesc, (kb | k) != 0);
-            }
-            }
-          }
-          umma_commit_pair(&xempty[xs], 0x3);
-        }
-        umma_commit_pair(&tfull[acc], 0x3);
-      }
-    }
-  } else {
-    // ------------------------------ epilogue (both CTAs): TMEM -> bias/relu/dropout -> bf16 -> HBM ----
-    const int quarter = warp & 3;
-    const int half = warp >> 2;
-    int it = 0;
-    for (int t = pair; t < num_pairs; t += npairs_grid, ++it) {
-      const int tile = 2 * t + (int)rank;
-      const int acc = it & 1;
-      mbar_wait(&tfull[acc], (it >> 1) & 1);
-      tc_fence_after();
-      const int row = tile * kBM + quarter * 32 + lane;
-      const bool row_ok = row < p.rows;
-      bf16* out_row = p.h + (size_t)row * kD;
-      uint32_t vbuf[2][32];
-      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kD + half * kColsPerWarp;
-      tmem_ld32(tbase, vbuf[0]);
-#pragma unroll
-      for (int cc = 0; cc < kChunks; ++cc) {
-        const int col0 = half * kColsPerWarp + cc * 32;
-        tmem_ld_wait();
-        if (cc + 1 < kChunks) tmem_ld32(tbase + (cc + 1) * 32, vbuf[(cc + 1) & 1]);
-        if (p.debug & 1) continue;
-        const uint32_t (&v)[32] = vbuf[cc & 1];
-        uint32_t packed[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(s_bias + col0 + j);
-          float f[4] = {fmaxf(__uint_as_float(v[j]) + bb.x, 0.f), fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f),
-                        fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.f)};
-          if (p.drop_thresh) {                       // the same hash and key as the streaming kernel: identical masks
-            uint32_t z = (seed ^ ((uint32_t)row * 64u + (uint32_t)((col0 + j) >> 2))) * 0x9E3779B1u;
-            z ^= z >> 15;
-            z *= 0x85ebca6bu;
-            z ^= z >> 13;
-            const unsigned long long w = (unsigned long long)z * 0xD6E8FEB86659FD93ull;
-            const uint32_t h0 = (uint32_t)w ^ (uint32_t)(w >> 32), h1 = (uint32_t)(w >> 29);
-            const uint32_t bits[4] = {h0 & 0xffffu, h0 >> 16, h1 & 0xffffu, h1 >> 16};
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              f[e] = (bits[e] >= p.drop_thresh) ? f[e] * p.keep_scale : 0.f;
-          }
-          packed[j / 2] = pack_bf16x2(f[0], f[1]);
-          packed[j / 2 + 1] = pack_bf16x2(f[2], f[3]);
-        }
-        if (row_ok && !((p.debug & 2) && packed[0] != 0x12345678u)) {
-          uint4* dst = reinterpret_cast<uint4*>(out_row + col0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(cluster_map(&tempty[acc], 0));     // the leader waits for both CTAs' sixteen warps
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                              // the leader's MMAs read the peer's shared memory: leave together
-  if (warp == kEpiWarps + 1) {
-    tc_fence_after();
-    tmem_dealloc_pair(tmem_base, 512);
   }
 }
 
@@ -555,18 +371,6 @@ int launch_pathnet_fwd(const bf16* x, const bf16* w1, const float* b1, bf16* h, 
     { const int rc_ = imp_ensure_smem((const void*)pathnet_fwd_kernel<XS, WS>, smem); if (rc_) return rc_; }         \
     IMP_LAUNCH("pathnet_fwd", st, pathnet_fwd_kernel<XS, WS><<<grid, kFwdThreads, smem, st>>>(tm_x, tm_w, p));      \
   } while (0)
-  static const int pair_mode = []() { const char* e = getenv("IMP_PATHNET_PAIR"); return e ? atoi(e) : 0; }();
-  if (pair_mode && kdim == kPairK && imp_num_sms() >= 2) {
-    CUtensorMap tm_wh;                               // a CTA's half of W1: boxes of [128 output columns][64 k]
-    if ((rc = imp_make_tmap_2d(&tm_wh, w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kdim, kD, (uint64_t)kdim * 2, kBK, 128,
-                               CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    static_assert(kPairSmem <= 227 * 1024, "pathnet_fwd_pair shared memory");
-    { const int rc_ = imp_ensure_smem((const void*)pathnet_fwd_pair_kernel, kPairSmem); if (rc_) return rc_; }
-    const int pairs = (p.num_tiles + 1) / 2;
-    const int grid_pair = 2 * min(pairs, imp_num_sms() / 2);
-    IMP_LAUNCH("pathnet_fwd", st, pathnet_fwd_pair_kernel<<<grid_pair, kFwdThreads, kPairSmem, st>>>(tm_x, tm_wh, p));
-    return IMP_OK;
-  }
   switch (cfg) {
     case 1: IMP_PF(8, 2); break;
     case 2: IMP_PF(6, 3); break;
