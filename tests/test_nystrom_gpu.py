@@ -4,6 +4,8 @@ form of token_tail.nystrom_short it replaces on the GPU -- same reduced matrices
 import pytest
 import torch
 
+from util_hotpath import record
+
 pytestmark = pytest.mark.gpu
 
 
@@ -36,9 +38,14 @@ def test_nystrom_core_matches_the_batched_form(n, d, bsz, monkeypatch):
     out_t, g_t = _run(q, k, v, m, iters, False, monkeypatch)
     out_d, g_d = _run(q.double(), k.double(), v.double(), m, iters, False, monkeypatch)
     # the kernel is as close to fp64 as the fp32 library form is (both are fp32 chains of ~30 products), within 2x + 1e-6
+    tag = "nystrom_core n=%d d=%d" % (n, d)
+    record("test_nystrom_gpu", tag + " output", _rel(out_k, out_d), 1e-4, "batched torch form in fp64",
+           "the fp32 library form it replaces: %.1e" % _rel(out_t, out_d))
     assert _rel(out_k, out_d) <= 2 * _rel(out_t, out_d) + 1e-6, (_rel(out_k, out_d), _rel(out_t, out_d))
     assert _rel(out_k, out_d) < 1e-4
     for a, b, c, name in zip(g_k, g_t, g_d, "qkv"):
+        record("test_nystrom_gpu", tag + " grad " + name, _rel(a, c), 1e-3, "batched torch form in fp64",
+               "the fp32 library form it replaces: %.1e" % _rel(b, c))
         assert _rel(a, c) <= 2 * _rel(b, c) + 1e-5, (name, _rel(a, c), _rel(b, c))
         assert _rel(a, c) < 1e-3, (name, _rel(a, c))
 
