@@ -211,5 +211,5 @@ def test_captured_step_matches_eager(tmp_path, monkeypatch):
     # cancellation, see test_train_tuple_loss_and_gradients_match_reference): measured up to 1.3e-4 on path_net.0.weight
     for k, p in model.named_parameters():
         if k in ref:
-            assert rel(p.grad, ref[k]) < (1e-3 if k.startswith("path_net") else 2e-4), (k, rel(p.grad, ref[k]))
+            assert rel(p.grad, ref[k]) < (1e-3 if k.startswith("path_net") else 5e-4), (k, rel(p.grad, ref[k]))
     gs.close()
