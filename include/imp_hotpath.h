@@ -192,6 +192,19 @@ int imp_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* 
                          const float* conv_w, int heads, int taps, int n_mat, int n_dim, int head_dim, int iters,
                          float* dmat, float* dscale, float* dv, float* dconv, void* stream);
 
+/* The reduced matrix of the short-sequence Nystrom layer itself (imp_b200.token_tail.nystrom_short; the three soft-maxes
+ * of ops/attention.py:105-110 coincide there).  q (already multiplied by dim_head^-0.5), k: (n_mat, n_tok, head_dim) fp32,
+ * n_tok < landmarks, n_tok <= 47.  With p = landmarks - n_tok zero tokens in front:
+ *   mat (n_mat, n_tok+1, n_tok+1) <- [[p/m, sqrt(p)/m 1^T], [sqrt(p) c, D]],  c_i, D_ij = soft-max over {p zeros, (q k^T)_i*};
+ *   rowmax, colmax (n_mat) <- the largest row / column sum of the full landmarks x landmarks matrix (the caller takes
+ *   their maxima over the batch for the scale s of imp_nystrom_core_fwd: ops/utils.py:119-121). */
+int imp_nystrom_build_fwd(const float* q, const float* k, int n_mat, int n_tok, int head_dim, int landmarks, float* mat,
+                          float* rowmax, float* colmax, void* stream);
+/* Backward: dmat like mat, drowmax / dcolmax (n_mat) -> dq, dk like q, k (the soft-max is recomputed; the gradients of
+ * the two maxima go to their arg-max row / column). */
+int imp_nystrom_build_bwd(const float* q, const float* k, const float* dmat, const float* drowmax, const float* dcolmax,
+                          int n_mat, int n_tok, int head_dim, int landmarks, float* dq, float* dk, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

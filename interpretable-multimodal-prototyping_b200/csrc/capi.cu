@@ -325,3 +325,14 @@ extern "C" int imp_nystrom_core_bwd(const float* mat, const float* inv_scale, co
   return launch_nystrom_core_bwd(mat, inv_scale, v, dy, saved, conv_w, heads, taps, n_mat, n_dim, head_dim, iters, dmat,
                                  dscale, dv, dconv, ST(stream));
 }
+extern "C" int imp_nystrom_build_fwd(const float* q, const float* k, int n_mat, int n_tok, int head_dim, int landmarks,
+                                     float* mat, float* rowmax, float* colmax, void* stream) {
+  if (!q || !k || !mat || !rowmax || !colmax) IMP_FAIL(IMP_ERR_ARG, "imp_nystrom_build_fwd: null pointer");
+  return launch_nystrom_build_fwd(q, k, n_mat, n_tok, head_dim, landmarks, mat, rowmax, colmax, ST(stream));
+}
+extern "C" int imp_nystrom_build_bwd(const float* q, const float* k, const float* dmat, const float* drowmax,
+                                     const float* dcolmax, int n_mat, int n_tok, int head_dim, int landmarks, float* dq,
+                                     float* dk, void* stream) {
+  if (!q || !k || !dmat || !drowmax || !dcolmax || !dq || !dk) IMP_FAIL(IMP_ERR_ARG, "imp_nystrom_build_bwd: null pointer");
+  return launch_nystrom_build_bwd(q, k, dmat, drowmax, dcolmax, n_mat, n_tok, head_dim, landmarks, dq, dk, ST(stream));
+}

@@ -64,3 +64,7 @@ int launch_nystrom_core_fwd(const float* mat, const float* inv_scale, const floa
 int launch_nystrom_core_bwd(const float* mat, const float* inv_scale, const float* v, const float* dy, const float* zs,
                             const float* conv_w, int heads, int taps, int BH, int N, int d, int iters, float* dmat,
                             float* dscale, float* dv, float* dconv, cudaStream_t st);
+int launch_nystrom_build_fwd(const float* q, const float* k, int BH, int n, int d, int landmarks, float* mat,
+                             float* rowmax, float* colmax, cudaStream_t st);
+int launch_nystrom_build_bwd(const float* q, const float* k, const float* dmat, const float* drow, const float* dcol,
+                             int BH, int n, int d, int landmarks, float* dq, float* dk, cudaStream_t st);

@@ -313,7 +313,191 @@ int ny_check(int BH, int N, int d, int iters, const char* who) {
   return IMP_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// The reduced matrix itself (token_tail.nystrom_short): from q (already scaled) and k of the n real tokens,
+//   s = q k^T;  soft-max over {p zero logits of the padded tokens, s_i*}:  c_i = e^{-max}/Z_i,  D_ij = e^{s_ij-max}/Z_i
+//   M = [[p/m, sqrt(p)/m 1^T], [sqrt(p) c, D]]   ((n+1) x (n+1)),
+// plus, per matrix, the largest row sum p c_i + sum_j D_ij and the largest column sum of the FULL m x m matrix
+// (p/m + sum_i c_i for a padded column, p/m + sum_i D_ij for a token): the caller takes their maxima over the batch for
+// the pseudo-inverse's initial scale (ops/utils.py:119-121) and autograd routes the gradient of that scale back into
+// the arg-max row / column here.  One CTA per (slide, head); ~35 forward and ~60 backward library launches per layer
+// call become one each.
+// ------------------------------------------------------------------------------------------
+constexpr int kNbThreads = 256;
+struct NyBuildParams {
+  const float* q;          // (BH, n, d) scaled queries
+  const float* k;          // (BH, n, d)
+  const float* dmat;       // (BH, n+1, n+1)      backward
+  const float* drow;       // (BH)                backward: gradient of rowmax
+  const float* dcol;       // (BH)                backward: gradient of colmax
+  float* mat;              // (BH, n+1, n+1)      forward
+  float* rowmax;           // (BH)
+  float* colmax;           // (BH)
+  float* dq;               // (BH, n, d)          backward
+  float* dk;
+  int n, d;
+  float p, inv_m;          // number of padded tokens, 1 / landmarks
+};
+
+// shared: Q, K [n][d+1], S [n][n+1] (s, then D), c [n], rsum [n], csum [n+1], arg[2]
+__device__ __forceinline__ void ny_build_common(const NyBuildParams& p, float* Q, float* K, float* S, float* c, float* rsum,
+                                                float* csum, int* arg) {
+  const int n = p.n, d = p.d, LQ = d + 1, LS = n + 1;
+  const float* q = p.q + (size_t)blockIdx.x * n * d;
+  const float* k = p.k + (size_t)blockIdx.x * n * d;
+  for (int idx = threadIdx.x; idx < n * d; idx += kNbThreads) {
+    const int i = idx / d, e = idx - i * d;
+    Q[i * LQ + e] = __ldg(q + idx);
+    K[i * LQ + e] = __ldg(k + idx);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < n * n; idx += kNbThreads) {
+    const int i = idx / n, j = idx - i * n;
+    float a = 0.f;
+    for (int e = 0; e < d; ++e) a = fmaf(Q[i * LQ + e], K[j * LQ + e], a);
+    S[i * LS + j] = a;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < n) {                       // thread = row: soft-max with p zero logits in front
+    const int i = threadIdx.x;
+    float mx = 0.f;
+    for (int j = 0; j < n; ++j) mx = fmaxf(mx, S[i * LS + j]);
+    float z = p.p * __expf(-mx);
+    for (int j = 0; j < n; ++j) { const float e = __expf(S[i * LS + j] - mx); S[i * LS + j] = e; z += e; }
+    const float iz = 1.f / z;
+    float rs = 0.f;
+    for (int j = 0; j < n; ++j) { const float v = S[i * LS + j] * iz; S[i * LS + j] = v; rs += v; }
+    c[i] = __expf(-mx) * iz;
+    rsum[i] = p.p * c[i] + rs;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x <= n) {                      // thread = column of the full matrix (0 = a padded token)
+    const int j = threadIdx.x;
+    float cs = p.p * p.inv_m;
+    if (j == 0) { for (int i = 0; i < n; ++i) cs += c[i]; }
+    else { for (int i = 0; i < n; ++i) cs += S[i * LS + j - 1]; }
+    csum[j] = cs;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {                           // first maximum wins, as in a left-to-right scan
+    int ra = 0, ca = 0;
+    for (int i = 1; i < n; ++i) if (rsum[i] > rsum[ra]) ra = i;
+    for (int j = 1; j <= n; ++j) if (csum[j] > csum[ca]) ca = j;
+    arg[0] = ra; arg[1] = ca;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kNbThreads) nystrom_build_fwd_kernel(const NyBuildParams p) {
+  extern __shared__ float nb_smem[];
+  const int n = p.n, d = p.d, LQ = d + 1, LS = n + 1, N = n + 1;
+  float* Q = nb_smem;
+  float* K = Q + n * LQ;
+  float* S = K + n * LQ;
+  float* c = S + n * LS;
+  float* rsum = c + n;
+  float* csum = rsum + n;
+  int* arg = reinterpret_cast<int*>(csum + n + 1);
+  ny_build_common(p, Q, K, S, c, rsum, csum, arg);
+  float* mat = p.mat + (size_t)blockIdx.x * N * N;
+  const float rp = sqrtf(p.p);
+  for (int idx = threadIdx.x; idx < N * N; idx += kNbThreads) {
+    const int i = idx / N, j = idx - i * N;
+    float v;
+    if (i == 0) v = (j == 0 ? p.p : rp) * p.inv_m;
+    else v = j == 0 ? rp * c[i - 1] : S[(i - 1) * LS + j - 1];
+    mat[idx] = v;
+  }
+  if (threadIdx.x == 0) {
+    p.rowmax[blockIdx.x] = rsum[arg[0]];
+    p.colmax[blockIdx.x] = csum[arg[1]];
+  }
+}
+
+__global__ void __launch_bounds__(kNbThreads) nystrom_build_bwd_kernel(const NyBuildParams p) {
+  extern __shared__ float nb_smem[];
+  const int n = p.n, d = p.d, LQ = d + 1, LS = n + 1, N = n + 1;
+  float* Q = nb_smem;
+  float* K = Q + n * LQ;
+  float* S = K + n * LQ;                            // D
+  float* c = S + n * LS;
+  float* rsum = c + n;
+  float* csum = rsum + n;
+  int* arg = reinterpret_cast<int*>(csum + n + 1);
+  float* G = reinterpret_cast<float*>(arg + 2);     // dD, then ds   [n][n+1]
+  float* dc = G + n * LS;                           // [n]
+  ny_build_common(p, Q, K, S, c, rsum, csum, arg);
+  const float* dmat = p.dmat + (size_t)blockIdx.x * N * N;
+  const float drow = __ldg(p.drow + blockIdx.x), dcol = __ldg(p.dcol + blockIdx.x);
+  const int ra = arg[0], ca = arg[1];
+  const float rp = sqrtf(p.p);
+  for (int idx = threadIdx.x; idx < n * n; idx += kNbThreads) {
+    const int i = idx / n, j = idx - i * n;
+    G[i * LS + j] = __ldg(dmat + (size_t)(i + 1) * N + j + 1) + (i == ra ? drow : 0.f) + (j + 1 == ca ? dcol : 0.f);
+  }
+  if ((int)threadIdx.x < n) {
+    const int i = threadIdx.x;
+    dc[i] = rp * __ldg(dmat + (size_t)(i + 1) * N) + (i == ra ? p.p * drow : 0.f) + (ca == 0 ? dcol : 0.f);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < n) {                       // ds_ij = D_ij (dD_ij - sum_k dD_ik D_ik - dc_i c_i)
+    const int i = threadIdx.x;
+    float inner = dc[i] * c[i];
+    for (int j = 0; j < n; ++j) inner = fmaf(G[i * LS + j], S[i * LS + j], inner);
+    for (int j = 0; j < n; ++j) G[i * LS + j] = S[i * LS + j] * (G[i * LS + j] - inner);
+  }
+  __syncthreads();
+  float* dq = p.dq + (size_t)blockIdx.x * n * d;
+  float* dk = p.dk + (size_t)blockIdx.x * n * d;
+  for (int idx = threadIdx.x; idx < n * d; idx += kNbThreads) {
+    const int i = idx / d, e = idx - i * d;
+    float a = 0.f, b = 0.f;
+    for (int j = 0; j < n; ++j) {
+      a = fmaf(G[i * LS + j], K[j * LQ + e], a);    // dq_i = sum_j ds_ij k_j
+      b = fmaf(G[j * LS + i], Q[j * LQ + e], b);    // dk_i = sum_j ds_ji q_j
+    }
+    dq[idx] = a;
+    dk[idx] = b;
+  }
+}
+
+static size_t ny_build_smem(int n, int d, bool bwd) {
+  size_t f = (size_t)2 * n * (d + 1) + (size_t)n * (n + 1) + n + n + (n + 1) + 2;
+  if (bwd) f += (size_t)n * (n + 1) + n;
+  return f * sizeof(float);
+}
+static int ny_build_check(int BH, int n, int d, int landmarks, const char* who) {
+  if (BH <= 0 || n < 1 || n > kNyMaxN - 1) IMP_FAIL(IMP_ERR_ARG, "%s: 1..%d tokens per matrix (got %d; %d matrices)", who, kNyMaxN - 1, n, BH);
+  if (d < 1 || d > 128) IMP_FAIL(IMP_ERR_ARG, "%s: head dim %d out of [1,128]", who, d);
+  if (landmarks <= n) IMP_FAIL(IMP_ERR_ARG, "%s: %d landmarks need more than the %d tokens", who, landmarks, n);
+  return IMP_OK;
+}
+
 }  // namespace
+
+int launch_nystrom_build_fwd(const float* q, const float* k, int BH, int n, int d, int landmarks, float* mat,
+                             float* rowmax, float* colmax, cudaStream_t st) {
+  { const int rc = ny_build_check(BH, n, d, landmarks, "nystrom_build_fwd"); if (rc) return rc; }
+  NyBuildParams p{};
+  p.q = q; p.k = k; p.mat = mat; p.rowmax = rowmax; p.colmax = colmax; p.n = n; p.d = d;
+  p.p = (float)(landmarks - n); p.inv_m = 1.f / (float)landmarks;
+  const size_t smem = ny_build_smem(n, d, false);
+  { const int rc = imp_ensure_smem((const void*)nystrom_build_fwd_kernel, 96 * 1024); if (rc) return rc; }
+  IMP_LAUNCH("nystrom_build_fwd", st, nystrom_build_fwd_kernel<<<BH, kNbThreads, smem, st>>>(p));
+  return IMP_OK;
+}
+
+int launch_nystrom_build_bwd(const float* q, const float* k, const float* dmat, const float* drow, const float* dcol,
+                             int BH, int n, int d, int landmarks, float* dq, float* dk, cudaStream_t st) {
+  { const int rc = ny_build_check(BH, n, d, landmarks, "nystrom_build_bwd"); if (rc) return rc; }
+  NyBuildParams p{};
+  p.q = q; p.k = k; p.dmat = dmat; p.drow = drow; p.dcol = dcol; p.dq = dq; p.dk = dk; p.n = n; p.d = d;
+  p.p = (float)(landmarks - n); p.inv_m = 1.f / (float)landmarks;
+  const size_t smem = ny_build_smem(n, d, true);
+  { const int rc = imp_ensure_smem((const void*)nystrom_build_bwd_kernel, 96 * 1024); if (rc) return rc; }
+  IMP_LAUNCH("nystrom_build_bwd", st, nystrom_build_bwd_kernel<<<BH, kNbThreads, smem, st>>>(p));
+  return IMP_OK;
+}
 
 size_t nystrom_core_saved_floats(int N, int iters) {
   const int NP = (N + 3) & ~3;

@@ -59,6 +59,13 @@ def nystrom_short(q, k, v, m: int, iters: int, conv_w=None):
     n = q.shape[-2]
     p = float(m - n)
     rp = math.sqrt(p)
+    if q.is_cuda and _core_supported(n + 1, v.shape[-1], iters) and q.shape[-1] <= 128:
+        # two kernels per direction (csrc/nystrom.cu): the reduced matrix with its row / column maxima, then the core.
+        # Only the batch-global scale stays in torch, so that autograd sends its gradient to the arg-max row / column.
+        mat, rowmax, colmax = _NystromBuild.apply(q, k, int(m))
+        rs = rowmax.max().clamp_min((p + n) / m)                 # padded rows sum to (p + n) / m = 1
+        inv_scale = 1.0 / (rs * colmax.max())
+        return _NystromCore.apply(mat, inv_scale, v, iters, None if conv_w is None else conv_w.reshape(conv_w.shape[0], -1))
     s = q @ k.transpose(-1, -2)                                  # (B,H,n,n) real-token block of q k^T
     smax = s.max(dim=-1, keepdim=True).values.clamp_min(0.0)     # padded columns have logit 0
     es = torch.exp(s - smax)
@@ -70,9 +77,6 @@ def nystrom_short(q, k, v, m: int, iters: int, conv_w=None):
     cs = torch.maximum((p / m + cvec.sum(-2)).max(), (p / m + dmat.sum(-2)).max())
     top = torch.cat([s.new_full(s.shape[:-2] + (1, 1), p / m), s.new_full(s.shape[:-2] + (1, n), rp / m)], dim=-1)
     mat = torch.cat([top, torch.cat([rp * cvec, dmat], dim=-1)], dim=-2)          # M(A), (B,H,n+1,n+1)
-    if mat.is_cuda and _core_supported(n + 1, v.shape[-1], iters):
-        # one kernel per direction instead of ~85 batched GEMMs and ~100 element-wise launches (csrc/nystrom.cu)
-        return _NystromCore.apply(mat, 1.0 / (rs * cs), v, iters, None if conv_w is None else conv_w.reshape(conv_w.shape[0], -1))
     eye = torch.eye(n + 1, device=s.device, dtype=s.dtype)
     z = mat.transpose(-1, -2) / (rs * cs)
     for _ in range(iters):
@@ -89,6 +93,38 @@ def _core_supported(n_dim: int, head_dim: int, iters: int) -> bool:
     """Shapes csrc/nystrom.cu holds in shared memory; anything else (more than 47 tokens: P = 64 prototypes) keeps
     the batched form above."""
     return n_dim <= 48 and head_dim in (32, 64) and 0 <= iters <= 8
+
+
+class _NystromBuild(torch.autograd.Function):
+    """(q scaled, k) (B,H,n,d) -> the reduced matrix M (B,H,n+1,n+1) and, per matrix, the largest row and column sum of
+    the full m x m soft-max matrix (differentiable: their gradients go to the arg-max row / column)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, q, k, m):
+        from . import _lib
+        q, k = q.contiguous(), k.contiguous()
+        b, h, n, d = q.shape
+        mat = torch.empty(b, h, n + 1, n + 1, device=q.device, dtype=torch.float32)
+        rowmax = torch.empty(b, h, device=q.device, dtype=torch.float32)
+        colmax = torch.empty(b, h, device=q.device, dtype=torch.float32)
+        _lib.call("imp_nystrom_build_fwd", q, k, b * h, n, d, int(m), mat, rowmax, colmax, _lib.stream_ptr())
+        ctx.save_for_backward(q, k)
+        ctx.m = int(m)
+        return mat, rowmax, colmax
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dmat, drow, dcol):
+        from . import _lib
+        q, k = ctx.saved_tensors
+        b, h, n, d = q.shape
+        dmat = torch.zeros(b, h, n + 1, n + 1, device=q.device) if dmat is None else dmat.contiguous().float()
+        drow = torch.zeros(b, h, device=q.device) if drow is None else drow.contiguous().float()
+        dcol = torch.zeros(b, h, device=q.device) if dcol is None else dcol.contiguous().float()
+        dq, dk = torch.empty_like(q), torch.empty_like(k)
+        _lib.call("imp_nystrom_build_bwd", q, k, dmat, drow, dcol, b * h, n, d, ctx.m, dq, dk, _lib.stream_ptr())
+        return dq, dk, None
 
 
 class _NystromCore(torch.autograd.Function):
